@@ -1,0 +1,126 @@
+"""ctypes binding of libgraphcast_b200.so (the C ABI in include/graphcast_b200.h).
+
+There is NO fallback: if the shared library is missing or does not export the
+ABI, importing the product path raises.  Build it with
+`graphcast_b200/csrc/build.sh` or `__graft_entry__.build()`.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                         "libgraphcast_b200.so")
+
+GCB_ABI_VERSION = 1
+GCB_MAX_MSG_STEPS = 64
+PREC_BF16X3, PREC_BF16, PREC_FP32_SIMT = 0, 1, 2
+PRECISIONS = {"bf16x3": PREC_BF16X3, "bf16": PREC_BF16, "fp32_simt": PREC_FP32_SIMT}
+ACT_NONE, ACT_SWISH = 0, 1
+
+_fp = C.c_void_p   # device pointers are passed as raw addresses
+
+
+class Segment(C.Structure):
+  _fields_ = [("table", _fp), ("idx", _fp), ("ld", C.c_int32), ("k", C.c_int32),
+              ("k_valid", C.c_int32), ("fan", C.c_int32)]
+
+
+class LayerDesc(C.Structure):
+  _fields_ = [("rows", C.c_int32), ("n", C.c_int32), ("n_valid", C.c_int32),
+              ("nseg", C.c_int32), ("seg", Segment * 3),
+              ("w_packed", _fp), ("w_f32", _fp), ("bias", _fp),
+              ("ln_scale", _fp), ("ln_offset", _fp), ("act", C.c_int32),
+              ("residual", _fp), ("ld_res", C.c_int32),
+              ("out", _fp), ("ld_out", C.c_int32),
+              ("out_y", _fp), ("ld_out_y", C.c_int32),
+              ("precision", C.c_int32)]
+
+
+class Mlp(C.Structure):
+  _fields_ = [("w0_packed", _fp), ("w0_f32", _fp), ("b0", _fp),
+              ("w1_packed", _fp), ("w1_f32", _fp), ("b1", _fp),
+              ("ln_scale", _fp), ("ln_offset", _fp),
+              ("k0", C.c_int32), ("n1", C.c_int32), ("n1_valid", C.c_int32)]
+
+
+class Model(C.Structure):
+  _fields_ = [
+      ("num_grid", C.c_int32), ("num_mesh", C.c_int32),
+      ("e_g2m", C.c_int32), ("e_mesh", C.c_int32), ("e_m2g", C.c_int32),
+      ("c_in_pad", C.c_int32), ("c_in_valid", C.c_int32),
+      ("msg_steps", C.c_int32), ("precision", C.c_int32),
+      ("g2m_snd", _fp), ("g2m_rcv", _fp), ("g2m_row_ptr", _fp), ("g2m_feat", _fp),
+      ("mesh_snd", _fp), ("mesh_rcv", _fp), ("mesh_row_ptr", _fp), ("mesh_feat", _fp),
+      ("m2g_snd", _fp), ("m2g_rcv", _fp), ("m2g_feat", _fp),
+      ("mesh_in", _fp),
+      ("enc_grid", Mlp), ("enc_mesh", Mlp), ("enc_e_g2m", Mlp), ("proc_e_g2m", Mlp),
+      ("proc_n_mesh_g2m", Mlp), ("proc_n_grid_g2m", Mlp),
+      ("enc_e_mesh", Mlp),
+      ("proc_e_mesh", Mlp * GCB_MAX_MSG_STEPS),
+      ("proc_n_mesh", Mlp * GCB_MAX_MSG_STEPS),
+      ("enc_e_m2g", Mlp), ("proc_e_m2g", Mlp), ("proc_n_grid_m2g", Mlp), ("dec_grid", Mlp),
+      ("hidden", _fp), ("edge_a", _fp), ("edge_b", _fp), ("grid_lat", _fp),
+      ("mesh_lat", _fp), ("mesh_agg", _fp), ("mesh_edge", _fp), ("mesh_msg", _fp),
+  ]
+
+
+# name -> (restype, argtypes); every symbol declared in include/graphcast_b200.h.
+EXPORTS = {
+    "gcb_abi_version": (C.c_int, []),
+    "gcb_last_error": (C.c_char_p, []),
+    "gcb_sm_count": (C.c_int, [C.c_int]),
+    "gcb_packed_weight_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "gcb_pack_weight_host": (C.c_int, [_fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _fp]),
+    "gcb_layer_forward": (C.c_int, [C.POINTER(LayerDesc), _fp]),
+    "gcb_segment_sum": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, _fp, C.c_int32, C.c_int32, _fp]),
+    "gcb_pack_grid_features": (C.c_int, [_fp, C.c_int32, C.c_int64, _fp, _fp, _fp, C.c_int32,
+                                         _fp, C.c_int32, _fp]),
+    "gcb_unpack_grid_outputs": (C.c_int, [_fp, C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp,
+                                          _fp, _fp, _fp]),
+    "gcb_forward": (C.c_int, [C.POINTER(Model), _fp, _fp, _fp, C.POINTER(C.c_int32)]),
+    "gcb_selftest_layer": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                     C.POINTER(C.c_float)]),
+}
+
+
+class NativeLibraryError(RuntimeError):
+  pass
+
+
+_lib = None
+
+
+def lib():
+  """Loads the shared library once; raises NativeLibraryError if unavailable."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.exists(_LIB_PATH):
+    raise NativeLibraryError(
+        f"{_LIB_PATH} not found: build it with graphcast_b200/csrc/build.sh "
+        "(there is no CPU / PyTorch fallback for the GraphCast hot path)")
+  try:
+    handle = C.CDLL(_LIB_PATH)
+  except OSError as e:
+    raise NativeLibraryError(f"cannot load {_LIB_PATH}: {e}") from e
+  for name, (restype, argtypes) in EXPORTS.items():
+    try:
+      fn = getattr(handle, name)
+    except AttributeError as e:
+      raise NativeLibraryError(f"{_LIB_PATH} does not export {name}") from e
+    fn.restype = restype
+    fn.argtypes = argtypes
+  if handle.gcb_abi_version() != GCB_ABI_VERSION:
+    raise NativeLibraryError("ABI version mismatch between _native.py and the library")
+  _lib = handle
+  return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+  if rc != 0:
+    msg = lib().gcb_last_error().decode("utf-8", "replace")
+    if rc == -1:
+      raise ValueError(f"{what}: {msg}")
+    raise RuntimeError(f"{what}: gcb status {rc}: {msg}")

@@ -1,0 +1,413 @@
+// C ABI of graphcast_b200 (see include/graphcast_b200.h): argument checking,
+// kernel launches and the orchestration of one GraphCast step.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/graphcast_b200.h"
+#include "aux_kernels.cuh"
+#include "mlp_simt.cuh"
+#include "mlp_tc.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define GCB_CHECK_ARG(cond, msg) \
+  do {                           \
+    if (!(cond)) return fail(GCB_ERR_INVALID, std::string("invalid argument: ") + (msg)); \
+  } while (0)
+
+#define GCB_CUDA(expr)                                                              \
+  do {                                                                              \
+    cudaError_t e_ = (expr);                                                        \
+    if (e_ != cudaSuccess)                                                          \
+      return fail(GCB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+uint16_t f32_to_bf16_rne(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);  // NaN
+  const uint32_t lsb = (u >> 16) & 1u;
+  u += 0x7fffu + lsb;
+  return static_cast<uint16_t>(u >> 16);
+}
+float bf16_to_f32(uint16_t h) {
+  uint32_t u = static_cast<uint32_t>(h) << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+int sm_count_cached() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+int validate_layer(const gcb_layer_desc* d) {
+  GCB_CHECK_ARG(d != nullptr, "null descriptor");
+  GCB_CHECK_ARG(d->rows >= 0, "rows < 0");
+  GCB_CHECK_ARG(d->n == 256 || d->n == 512, "n must be 256 or 512");
+  GCB_CHECK_ARG(d->n_valid > 0 && d->n_valid <= d->n, "n_valid out of range");
+  GCB_CHECK_ARG(d->nseg >= 1 && d->nseg <= 3, "nseg must be 1..3");
+  int ksteps = 0;
+  for (int s = 0; s < d->nseg; ++s) {
+    const gcb_segment& g = d->seg[s];
+    GCB_CHECK_ARG(g.table != nullptr && aligned16(g.table), "segment table null/unaligned");
+    GCB_CHECK_ARG(g.k > 0 && g.k % 16 == 0, "segment k must be a positive multiple of 16");
+    GCB_CHECK_ARG(g.k_valid > 0 && g.k_valid <= g.k && g.k_valid % 4 == 0,
+                  "segment k_valid must be a multiple of 4 and <= k");
+    GCB_CHECK_ARG(g.ld % 4 == 0 && g.ld >= g.k_valid, "segment ld must be a multiple of 4 and >= k_valid");
+    GCB_CHECK_ARG(g.fan >= 1, "segment fan must be >= 1");
+    ksteps += g.k / 16;
+  }
+  GCB_CHECK_ARG(ksteps <= gcb::kMaxKSteps, "K too large");
+  GCB_CHECK_ARG(d->bias != nullptr, "bias is null");
+  GCB_CHECK_ARG((d->ln_scale == nullptr) == (d->ln_offset == nullptr), "ln_scale/ln_offset mismatch");
+  GCB_CHECK_ARG(d->out != nullptr || d->out_y != nullptr, "no output");
+  if (d->out) GCB_CHECK_ARG(aligned16(d->out) && d->ld_out % 4 == 0 && d->ld_out >= d->n_valid, "out unaligned");
+  if (d->out_y) GCB_CHECK_ARG(aligned16(d->out_y) && d->ld_out_y % 4 == 0 && d->ld_out_y >= d->n_valid, "out_y unaligned");
+  if (d->residual) GCB_CHECK_ARG(aligned16(d->residual) && d->ld_res % 4 == 0, "residual unaligned");
+  GCB_CHECK_ARG(d->act == GCB_ACT_NONE || d->act == GCB_ACT_SWISH, "unknown activation");
+  if (d->precision == GCB_PREC_FP32_SIMT) {
+    GCB_CHECK_ARG(d->w_f32 != nullptr, "w_f32 is null (FP32_SIMT)");
+  } else {
+    GCB_CHECK_ARG(d->precision == GCB_PREC_BF16X3 || d->precision == GCB_PREC_BF16, "unknown precision");
+    GCB_CHECK_ARG(d->w_packed != nullptr && aligned16(d->w_packed), "w_packed null/unaligned");
+  }
+  return GCB_OK;
+}
+
+template <bool kSplit>
+int launch_tc(const gcb_layer_desc& d, cudaStream_t stream) {
+  using Cfg = gcb::TcConfig<kSplit>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  GCB_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    GCB_CUDA(cudaFuncSetAttribute(gcb::mlp_layer_tc_kernel<kSplit>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set[dev] = true;
+  }
+  const int tiles = (d.rows + gcb::kTileM - 1) / gcb::kTileM;
+  const int grid = tiles < sm_count_cached() ? tiles : sm_count_cached();
+  gcb::mlp_layer_tc_kernel<kSplit><<<grid, gcb::kThreads, Cfg::kSmemBytes, stream>>>(d);
+  GCB_CUDA(cudaGetLastError());
+  return GCB_OK;
+}
+
+int launch_simt(const gcb_layer_desc& d, cudaStream_t stream) {
+  const size_t smem = (static_cast<size_t>(gcb::kSimtRows) * d.n + gcb::kSimtRows * 17 +
+                       static_cast<size_t>(gcb::kSimtK) * d.n) * sizeof(float);
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  GCB_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    GCB_CUDA(cudaFuncSetAttribute(gcb::mlp_layer_simt_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    attr_set[dev] = true;
+  }
+  const int grid = (d.rows + gcb::kSimtRows - 1) / gcb::kSimtRows;
+  gcb::mlp_layer_simt_kernel<<<grid, gcb::kSimtThreads, smem, stream>>>(d);
+  GCB_CUDA(cudaGetLastError());
+  return GCB_OK;
+}
+
+struct StepCtx {
+  const gcb_model* m;
+  cudaStream_t stream;
+  int launches;
+};
+
+gcb_segment seg(const float* table, const int32_t* idx, int ld, int k, int k_valid, int fan = 1) {
+  gcb_segment s;
+  s.table = table; s.idx = idx; s.ld = ld; s.k = k; s.k_valid = k_valid; s.fan = fan;
+  return s;
+}
+
+// Two-layer MLP: hidden = swish(concat(segs) @ W0 + b0);  y = [LN](hidden @ W1 + b1).
+int run_mlp(StepCtx& c, const gcb_mlp& w, int rows, int nseg, const gcb_segment* segs,
+            const float* residual, float* out, int ld_out, float* out_y) {
+  if (rows == 0) return GCB_OK;
+  gcb_layer_desc l0;
+  memset(&l0, 0, sizeof(l0));
+  l0.rows = rows; l0.n = 512; l0.n_valid = 512; l0.nseg = nseg;
+  int k0 = 0;
+  for (int s = 0; s < nseg; ++s) { l0.seg[s] = segs[s]; k0 += segs[s].k; }
+  if (k0 != w.k0) return fail(GCB_ERR_INVALID, "run_mlp: segment widths do not match the weight");
+  l0.w_packed = w.w0_packed; l0.w_f32 = w.w0_f32; l0.bias = w.b0;
+  l0.act = GCB_ACT_SWISH;
+  l0.out = c.m->hidden; l0.ld_out = 512;
+  l0.precision = c.m->precision;
+  int rc = gcb_layer_forward(&l0, c.stream);
+  if (rc) return rc;
+  gcb_layer_desc l1;
+  memset(&l1, 0, sizeof(l1));
+  l1.rows = rows; l1.n = w.n1; l1.n_valid = w.n1_valid; l1.nseg = 1;
+  l1.seg[0] = seg(c.m->hidden, nullptr, 512, 512, 512);
+  l1.w_packed = w.w1_packed; l1.w_f32 = w.w1_f32; l1.bias = w.b1;
+  l1.ln_scale = w.ln_scale; l1.ln_offset = w.ln_offset;
+  l1.act = GCB_ACT_NONE;
+  l1.residual = residual; l1.ld_res = 512;
+  l1.out = out; l1.ld_out = ld_out;
+  l1.out_y = out_y; l1.ld_out_y = 512;
+  l1.precision = c.m->precision;
+  rc = gcb_layer_forward(&l1, c.stream);
+  if (rc) return rc;
+  c.launches += 2;
+  return GCB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gcb_abi_version(void) { return GCB_ABI_VERSION; }
+
+const char* gcb_last_error(void) { return g_err.c_str(); }
+
+int gcb_sm_count(int device) {
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
+  return n;
+}
+
+int64_t gcb_packed_weight_bytes(int32_t k, int32_t n) {
+  if (k <= 0 || n <= 0 || k % 16 != 0) return -1;
+  return static_cast<int64_t>(k) * n * 4;   // bf16 hi + bf16 lo per element
+}
+
+int gcb_pack_weight_host(const float* w, int32_t k_rows, int32_t n_cols, int32_t k, int32_t n,
+                         void* dst) {
+  GCB_CHECK_ARG(w != nullptr && dst != nullptr, "null pointer");
+  GCB_CHECK_ARG(k > 0 && k % 16 == 0 && n > 0 && n % 8 == 0, "k must be a multiple of 16, n of 8");
+  GCB_CHECK_ARG(k_rows <= k && n_cols <= n && k_rows >= 0 && n_cols >= 0, "real shape exceeds padded shape");
+  uint16_t* img = static_cast<uint16_t*>(dst);
+  const int ksteps = k / 16;
+  for (int ks = 0; ks < ksteps; ++ks) {
+    uint16_t* hi = img + static_cast<size_t>(ks) * n * 32;   // n*64 bytes per K-step
+    uint16_t* lo = hi + static_cast<size_t>(n) * 16;
+    for (int c = 0; c < 2; ++c)
+      for (int nn = 0; nn < n; ++nn)
+        for (int j = 0; j < 8; ++j) {
+          const int kk = ks * 16 + c * 8 + j;
+          const float v = (kk < k_rows && nn < n_cols) ? w[static_cast<size_t>(kk) * n_cols + nn] : 0.f;
+          const uint16_t h = f32_to_bf16_rne(v);
+          const uint16_t l = f32_to_bf16_rne(v - bf16_to_f32(h));
+          const size_t off = (static_cast<size_t>(c) * n + nn) * 8 + j;
+          hi[off] = h;
+          lo[off] = l;
+        }
+  }
+  return GCB_OK;
+}
+
+int gcb_layer_forward(const gcb_layer_desc* d, void* stream) {
+  int rc = validate_layer(d);
+  if (rc) return rc;
+  if (d->rows == 0) return GCB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (d->precision) {
+    case GCB_PREC_BF16X3: return launch_tc<true>(*d, st);
+    case GCB_PREC_BF16: return launch_tc<false>(*d, st);
+    default: return launch_simt(*d, st);
+  }
+}
+
+int gcb_segment_sum(const float* msg, int32_t ld_msg, const int32_t* row_ptr, int32_t num_nodes,
+                    float* out, int32_t ld_out, int32_t width, void* stream) {
+  GCB_CHECK_ARG(msg && row_ptr && out, "null pointer");
+  GCB_CHECK_ARG(width == 512, "segment_sum supports width 512");
+  GCB_CHECK_ARG(ld_msg % 4 == 0 && ld_out % 4 == 0 && aligned16(msg) && aligned16(out), "unaligned");
+  if (num_nodes == 0) return GCB_OK;
+  const int warps_per_block = 8;
+  long long blocks = (static_cast<long long>(num_nodes) + warps_per_block - 1) / warps_per_block;
+  const long long cap = static_cast<long long>(sm_count_cached()) * 16;
+  if (blocks > cap) blocks = cap;
+  gcb::segment_sum_kernel<4><<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      msg, ld_msg, row_ptr, num_nodes, out, ld_out);
+  GCB_CUDA(cudaGetLastError());
+  return GCB_OK;
+}
+
+int gcb_pack_grid_features(const float* planes, int32_t n_ch, int64_t n_nodes, const float* mean,
+                           const float* scale, const float* node_static, int32_t n_static,
+                           float* feats, int32_t ld, void* stream) {
+  GCB_CHECK_ARG(planes && feats, "null pointer");
+  GCB_CHECK_ARG(n_ch > 0 && n_static >= 0 && ld >= n_ch + n_static, "ld too small");
+  GCB_CHECK_ARG(n_static == 0 || node_static != nullptr, "node_static is null");
+  if (n_nodes == 0) return GCB_OK;
+  dim3 grid(static_cast<unsigned>((n_nodes + 31) / 32), static_cast<unsigned>((ld + 31) / 32));
+  gcb::pack_grid_features_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      planes, n_ch, n_nodes, mean, scale, node_static, n_static, feats, ld);
+  GCB_CUDA(cudaGetLastError());
+  return GCB_OK;
+}
+
+int gcb_unpack_grid_outputs(const float* y, int32_t ld_y, int32_t n_out, int64_t n_nodes,
+                            const float* scale, const float* offset, const float* add_planes,
+                            const int32_t* add_plane_index, float* planes_out, void* stream) {
+  GCB_CHECK_ARG(y && planes_out, "null pointer");
+  GCB_CHECK_ARG(n_out > 0 && ld_y >= n_out, "ld_y too small");
+  GCB_CHECK_ARG((add_planes == nullptr) == (add_plane_index == nullptr), "add_planes/index mismatch");
+  if (n_nodes == 0) return GCB_OK;
+  dim3 grid(static_cast<unsigned>((n_nodes + 31) / 32), static_cast<unsigned>((n_out + 31) / 32));
+  gcb::unpack_grid_outputs_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      y, ld_y, n_out, n_nodes, scale, offset, add_planes, add_plane_index, planes_out);
+  GCB_CUDA(cudaGetLastError());
+  return GCB_OK;
+}
+
+int gcb_forward(const gcb_model* m, const float* grid_in, float* grid_out, void* stream,
+                int32_t* launches) {
+  GCB_CHECK_ARG(m && grid_in && grid_out, "null pointer");
+  GCB_CHECK_ARG(m->msg_steps >= 1 && m->msg_steps <= GCB_MAX_MSG_STEPS, "msg_steps out of range");
+  GCB_CHECK_ARG(m->e_m2g == 3 * m->num_grid, "mesh2grid must have fan-in 3");
+  StepCtx c{m, static_cast<cudaStream_t>(stream), 0};
+  int rc;
+  gcb_segment s[3];
+  const int D = 512;
+
+  // ---------------- encoder: grid2mesh_gnn (graphcast.py:550-604) ----------------
+  // vg0 = LN.MLP(grid_in)  -> grid_lat
+  s[0] = seg(grid_in, nullptr, m->c_in_pad, m->c_in_pad, m->c_in_valid);
+  if ((rc = run_mlp(c, m->enc_grid, m->num_grid, 1, s, nullptr, m->grid_lat, D, nullptr))) return rc;
+  // vm0 = LN.MLP(mesh_in)  -> mesh_lat
+  s[0] = seg(m->mesh_in, nullptr, m->c_in_pad, m->c_in_pad, m->c_in_valid);
+  if ((rc = run_mlp(c, m->enc_mesh, m->num_mesh, 1, s, nullptr, m->mesh_lat, D, nullptr))) return rc;
+  // e1 = LN.MLP(g2m edge feats)  -> edge_a
+  s[0] = seg(m->g2m_feat, nullptr, 4, 16, 4);
+  if ((rc = run_mlp(c, m->enc_e_g2m, m->e_g2m, 1, s, nullptr, m->edge_a, D, nullptr))) return rc;
+  // m1 = LN.MLP([e1 | vg0[snd] | vm0[rcv]])  -> edge_b   (edge residual e1+m1 is dead)
+  s[0] = seg(m->edge_a, nullptr, D, D, D);
+  s[1] = seg(m->grid_lat, m->g2m_snd, D, D, D);
+  s[2] = seg(m->mesh_lat, m->g2m_rcv, D, D, D);
+  if ((rc = run_mlp(c, m->proc_e_g2m, m->e_g2m, 3, s, nullptr, m->edge_b, D, nullptr))) return rc;
+  // agg1 = segment_sum(m1)
+  if ((rc = gcb_segment_sum(m->edge_b, D, m->g2m_row_ptr, m->num_mesh, m->mesh_agg, D, D, stream))) return rc;
+  c.launches += 1;
+  // vm1 = vm0 + LN.MLP([vm0 | agg1])  (in place)
+  s[0] = seg(m->mesh_lat, nullptr, D, D, D);
+  s[1] = seg(m->mesh_agg, nullptr, D, D, D);
+  if ((rc = run_mlp(c, m->proc_n_mesh_g2m, m->num_mesh, 2, s, m->mesh_lat, m->mesh_lat, D, nullptr))) return rc;
+  // vg1 = vg0 + LN.MLP([vg0])  (in place; grid nodes receive nothing in grid2mesh)
+  s[0] = seg(m->grid_lat, nullptr, D, D, D);
+  if ((rc = run_mlp(c, m->proc_n_grid_g2m, m->num_grid, 1, s, m->grid_lat, m->grid_lat, D, nullptr))) return rc;
+
+  // ---------------- processor: mesh_gnn (graphcast.py:606-639) --------------------
+  s[0] = seg(m->mesh_feat, nullptr, 4, 16, 4);
+  if ((rc = run_mlp(c, m->enc_e_mesh, m->e_mesh, 1, s, nullptr, m->mesh_edge, D, nullptr))) return rc;
+  for (int k = 0; k < m->msg_steps; ++k) {
+    const bool last = (k == m->msg_steps - 1);
+    // m = LN.MLP([e | v[snd] | v[rcv]]) -> mesh_msg;  e += m (skipped on the last
+    // step: the updated edge latents are never read again).
+    s[0] = seg(m->mesh_edge, nullptr, D, D, D);
+    s[1] = seg(m->mesh_lat, m->mesh_snd, D, D, D);
+    s[2] = seg(m->mesh_lat, m->mesh_rcv, D, D, D);
+    if ((rc = run_mlp(c, m->proc_e_mesh[k], m->e_mesh, 3, s, last ? nullptr : m->mesh_edge,
+                      last ? nullptr : m->mesh_edge, D, m->mesh_msg))) return rc;
+    if ((rc = gcb_segment_sum(m->mesh_msg, D, m->mesh_row_ptr, m->num_mesh, m->mesh_agg, D, D, stream))) return rc;
+    c.launches += 1;
+    // v += LN.MLP([v | agg])
+    s[0] = seg(m->mesh_lat, nullptr, D, D, D);
+    s[1] = seg(m->mesh_agg, nullptr, D, D, D);
+    if ((rc = run_mlp(c, m->proc_n_mesh[k], m->num_mesh, 2, s, m->mesh_lat, m->mesh_lat, D, nullptr))) return rc;
+  }
+
+  // ---------------- decoder: mesh2grid_gnn (graphcast.py:641-678) ------------------
+  s[0] = seg(m->m2g_feat, nullptr, 4, 16, 4);
+  if ((rc = run_mlp(c, m->enc_e_m2g, m->e_m2g, 1, s, nullptr, m->edge_a, D, nullptr))) return rc;
+  // m3 = LN.MLP([e3 | v[snd] | vg1[rcv]]) -> edge_b
+  s[0] = seg(m->edge_a, nullptr, D, D, D);
+  s[1] = seg(m->mesh_lat, m->m2g_snd, D, D, D);
+  s[2] = seg(m->grid_lat, m->m2g_rcv, D, D, D);
+  if ((rc = run_mlp(c, m->proc_e_m2g, m->e_m2g, 3, s, nullptr, m->edge_b, D, nullptr))) return rc;
+  // vg2 = vg1 + LN.MLP([vg1 | sum of the 3 incoming messages])  (in place)
+  s[0] = seg(m->grid_lat, nullptr, D, D, D);
+  s[1] = seg(m->edge_b, nullptr, D, D, D, /*fan=*/3);
+  if ((rc = run_mlp(c, m->proc_n_grid_m2g, m->num_grid, 2, s, m->grid_lat, m->grid_lat, D, nullptr))) return rc;
+  // out = MLP(vg2), no LayerNorm (deep_typed_graph_net.py:314-322)
+  s[0] = seg(m->grid_lat, nullptr, D, D, D);
+  if ((rc = run_mlp(c, m->dec_grid, m->num_grid, 1, s, nullptr, grid_out, 256, nullptr))) return rc;
+
+  if (launches) *launches = c.launches;
+  return GCB_OK;
+}
+
+int gcb_selftest_layer(int32_t rows, int32_t k, int32_t n, int32_t precision, float* rel_err) {
+  GCB_CHECK_ARG(rows > 0 && k > 0 && k % 16 == 0 && (n == 256 || n == 512) && rel_err, "bad shape");
+  std::vector<float> ha(static_cast<size_t>(rows) * k), hw(static_cast<size_t>(k) * n), hb(n), hs(n), ho(n);
+  uint32_t st = 12345u;
+  auto rnd = [&]() { st = st * 1664525u + 1013904223u; return (static_cast<float>(st >> 8) / 8388608.0f) - 1.0f; };
+  for (auto& v : ha) v = rnd();
+  const float wscale = 1.0f / sqrtf(static_cast<float>(k));
+  for (auto& v : hw) v = rnd() * wscale;
+  for (int i = 0; i < n; ++i) { hb[i] = 0.1f * rnd(); hs[i] = 1.0f + 0.1f * rnd(); ho[i] = 0.1f * rnd(); }
+  std::vector<uint8_t> himg(static_cast<size_t>(gcb_packed_weight_bytes(k, n)));
+  int rc = gcb_pack_weight_host(hw.data(), k, n, k, n, himg.data());
+  if (rc) return rc;
+  float *da = nullptr, *dw = nullptr, *db = nullptr, *ds = nullptr, *dof = nullptr, *o1 = nullptr, *o2 = nullptr;
+  void* dimg = nullptr;
+  GCB_CUDA(cudaMalloc(&da, ha.size() * 4));
+  GCB_CUDA(cudaMalloc(&dw, hw.size() * 4));
+  GCB_CUDA(cudaMalloc(&db, n * 4));
+  GCB_CUDA(cudaMalloc(&ds, n * 4));
+  GCB_CUDA(cudaMalloc(&dof, n * 4));
+  GCB_CUDA(cudaMalloc(&o1, static_cast<size_t>(rows) * n * 4));
+  GCB_CUDA(cudaMalloc(&o2, static_cast<size_t>(rows) * n * 4));
+  GCB_CUDA(cudaMalloc(&dimg, himg.size()));
+  GCB_CUDA(cudaMemcpy(da, ha.data(), ha.size() * 4, cudaMemcpyHostToDevice));
+  GCB_CUDA(cudaMemcpy(dw, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice));
+  GCB_CUDA(cudaMemcpy(db, hb.data(), n * 4, cudaMemcpyHostToDevice));
+  GCB_CUDA(cudaMemcpy(ds, hs.data(), n * 4, cudaMemcpyHostToDevice));
+  GCB_CUDA(cudaMemcpy(dof, ho.data(), n * 4, cudaMemcpyHostToDevice));
+  GCB_CUDA(cudaMemcpy(dimg, himg.data(), himg.size(), cudaMemcpyHostToDevice));
+  gcb_layer_desc d;
+  memset(&d, 0, sizeof(d));
+  d.rows = rows; d.n = n; d.n_valid = n; d.nseg = 1;
+  d.seg[0].table = da; d.seg[0].ld = k; d.seg[0].k = k; d.seg[0].k_valid = k; d.seg[0].fan = 1;
+  d.w_packed = dimg; d.w_f32 = dw; d.bias = db; d.ln_scale = ds; d.ln_offset = dof;
+  d.act = GCB_ACT_NONE;
+  d.out = o1; d.ld_out = n;
+  d.precision = precision;
+  rc = gcb_layer_forward(&d, nullptr);
+  if (rc) return rc;
+  d.out = o2; d.precision = GCB_PREC_FP32_SIMT;
+  rc = gcb_layer_forward(&d, nullptr);
+  if (rc) return rc;
+  GCB_CUDA(cudaDeviceSynchronize());
+  std::vector<float> r1(static_cast<size_t>(rows) * n), r2(r1.size());
+  GCB_CUDA(cudaMemcpy(r1.data(), o1, r1.size() * 4, cudaMemcpyDeviceToHost));
+  GCB_CUDA(cudaMemcpy(r2.data(), o2, r2.size() * 4, cudaMemcpyDeviceToHost));
+  double maxd = 0, maxr = 0;
+  for (size_t i = 0; i < r1.size(); ++i) {
+    const double dd = fabs(static_cast<double>(r1[i]) - r2[i]);
+    if (!(dd <= maxd)) maxd = dd;   // propagates NaN
+    if (fabs(r2[i]) > maxr) maxr = fabs(r2[i]);
+  }
+  *rel_err = static_cast<float>(maxd / (maxr > 0 ? maxr : 1.0));
+  cudaFree(da); cudaFree(dw); cudaFree(db); cudaFree(ds); cudaFree(dof); cudaFree(o1); cudaFree(o2); cudaFree(dimg);
+  return GCB_OK;
+}
+
+}  // extern "C"

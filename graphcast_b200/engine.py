@@ -1,0 +1,287 @@
+"""Device engine: uploads the static graph and weights, owns the HBM workspace and
+drives the C ABI (`gcb_forward`) for one GraphCast instance on one GPU.
+
+PyTorch is used for device memory and streams only; all arithmetic of the step
+runs in libgraphcast_b200.so.  HBM layout (fp32 unless noted):
+
+  grid_in    [Ng, c_in_pad]     packed, normalised inputs + 3 structural + zero pad
+  grid_lat   [Ng, 512]          latent grid nodes (updated in place vg0->vg1->vg2)
+  mesh_lat   [Nm, 512]          latent mesh nodes (updated in place, 1 + 16 times)
+  mesh_agg   [Nm, 512]          segment sums
+  mesh_edge  [E_mesh, 512]      latent multi-mesh edges (receiver-sorted order)
+  mesh_msg   [E_mesh, 512]      messages of the current step
+  edge_a/b   [max(E_g2m,E_m2g), 512]  bipartite edge latents / messages
+  hidden     [max rows, 512]    hidden activations between the two layers of an MLP
+  grid_out   [Ng, 256]          decoder output (n_out valid columns)
+  weights    per linear layer: bf16 hi|lo tile image (tcgen05 B operand) + fp32 copy
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Mapping, Optional
+
+import numpy as np
+import torch
+
+from graphcast_b200 import _native
+from graphcast_b200 import graph as graph_lib
+
+LATENT = 512
+
+
+def _ceil(x: int, m: int) -> int:
+  return (x + m - 1) // m * m
+
+
+def mlp_stem(gnn: str, prefix: str, set_name: str) -> str:
+  """Haiku module path stem of one MLP (reference deep_typed_graph_net.py:205-208,
+  251-262, 295-307, 315-319; gnn names graphcast.py:217,233,261)."""
+  return f"{gnn}/~_networks_builder/{prefix}{set_name}"
+
+
+class Engine:
+  """One GraphCast model resident on one CUDA device."""
+
+  def __init__(self, static_graph: graph_lib.StaticGraph,
+               params: Mapping[str, Mapping[str, np.ndarray]], *,
+               c_in: int, n_out: int, msg_steps: int, precision: str = "bf16x3",
+               device: Optional[torch.device] = None):
+    if precision not in _native.PRECISIONS:
+      raise ValueError(f"unknown precision {precision!r}; expected one of "
+                       f"{sorted(_native.PRECISIONS)}")
+    self._lib = _native.lib()            # raises if the CUDA library is missing
+    if not torch.cuda.is_available():
+      raise RuntimeError("graphcast_b200 requires a CUDA device (no CPU fallback)")
+    self.device = torch.device(device if device is not None else
+                               f"cuda:{torch.cuda.current_device()}")
+    if not 1 <= msg_steps <= _native.GCB_MAX_MSG_STEPS:
+      raise ValueError("gnn_msg_steps out of range")
+    if n_out > 256:
+      raise ValueError("at most 256 output channels are supported")
+    self.c_in = c_in                      # data channels (without structural)
+    self.n_out = n_out
+    self.msg_steps = msg_steps
+    self.precision = precision
+    self.c_in_pad = _ceil(c_in + 3, 16)
+    self.c_in_valid = _ceil(c_in + 3, 4)
+    g = static_graph
+    self.num_grid, self.num_mesh = g.num_grid_nodes, g.num_mesh_nodes
+    self._keep = []                       # device tensors referenced by raw pointer
+    self._model = _native.Model()
+    self._upload_graph(g)
+    self._upload_weights(params)
+    self._alloc_workspace()
+    self.launches_per_step = 0
+
+  # -- helpers -------------------------------------------------------------------
+  def _dev(self, array: np.ndarray, dtype) -> torch.Tensor:
+    t = torch.as_tensor(np.ascontiguousarray(array)).to(dtype).to(self.device)
+    self._keep.append(t)
+    return t
+
+  @staticmethod
+  def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+  # -- static graph --------------------------------------------------------------
+  def _upload_graph(self, g: graph_lib.StaticGraph) -> None:
+    m = self._model
+    m.num_grid, m.num_mesh = g.num_grid_nodes, g.num_mesh_nodes
+    # grid2mesh and multi-mesh edges in receiver-sorted execution order.
+    p1, s1, r1, rp1 = graph_lib.receiver_sorted(g.g2m_senders, g.g2m_receivers, g.num_mesh_nodes)
+    p2, s2, r2, rp2 = graph_lib.receiver_sorted(g.mesh_senders, g.mesh_receivers, g.num_mesh_nodes)
+    expected = np.repeat(np.arange(g.num_grid_nodes, dtype=np.int64), 3)
+    if g.m2g_receivers.shape[0] != expected.shape[0] or not np.array_equal(
+        g.m2g_receivers.astype(np.int64), expected):
+      raise ValueError("mesh2grid edges must be grouped by grid node with fan-in 3")
+    m.e_g2m, m.e_mesh, m.e_m2g = len(s1), len(s2), len(g.m2g_senders)
+    self.g2m_snd, self.g2m_rcv = self._dev(s1, torch.int32), self._dev(r1, torch.int32)
+    self.g2m_row_ptr = self._dev(rp1, torch.int32)
+    self.g2m_feat = self._dev(g.g2m_edge_feats[p1], torch.float32)
+    self.mesh_snd, self.mesh_rcv = self._dev(s2, torch.int32), self._dev(r2, torch.int32)
+    self.mesh_row_ptr = self._dev(rp2, torch.int32)
+    self.mesh_feat = self._dev(g.mesh_edge_feats[p2], torch.float32)
+    self.m2g_snd = self._dev(g.m2g_senders, torch.int32)
+    self.m2g_rcv = self._dev(g.m2g_receivers, torch.int32)
+    self.m2g_feat = self._dev(g.m2g_edge_feats, torch.float32)
+    # Mesh-node encoder input: zeros for the data channels + 3 structural
+    # features (reference graphcast.py:573-583).
+    mesh_in = np.zeros([g.num_mesh_nodes, self.c_in_pad], np.float32)
+    mesh_in[:, self.c_in:self.c_in + 3] = g.mesh_node_feats
+    self.mesh_in = self._dev(mesh_in, torch.float32)
+    self.grid_static = self._dev(g.grid_node_feats, torch.float32)   # [Ng,3]
+    m.g2m_snd, m.g2m_rcv = self._ptr(self.g2m_snd), self._ptr(self.g2m_rcv)
+    m.g2m_row_ptr, m.g2m_feat = self._ptr(self.g2m_row_ptr), self._ptr(self.g2m_feat)
+    m.mesh_snd, m.mesh_rcv = self._ptr(self.mesh_snd), self._ptr(self.mesh_rcv)
+    m.mesh_row_ptr, m.mesh_feat = self._ptr(self.mesh_row_ptr), self._ptr(self.mesh_feat)
+    m.m2g_snd, m.m2g_rcv = self._ptr(self.m2g_snd), self._ptr(self.m2g_rcv)
+    m.m2g_feat = self._ptr(self.m2g_feat)
+    m.mesh_in = self._ptr(self.mesh_in)
+    m.c_in_pad, m.c_in_valid = self.c_in_pad, self.c_in_valid
+    m.msg_steps = self.msg_steps
+    m.precision = _native.PRECISIONS[self.precision]
+
+  # -- weights ---------------------------------------------------------------------
+  def _pack_linear(self, w: np.ndarray, seg_real, seg_pad, n_pad: int):
+    """w [sum(seg_real), n_real] -> (packed image tensor, fp32 padded tensor).
+
+    Rows are re-laid so that segment s occupies seg_pad[s] rows (zero padded)."""
+    w = np.asarray(w, np.float32)
+    k_real, n_real = w.shape
+    if k_real != sum(seg_real):
+      raise ValueError(f"weight has {k_real} input rows, expected {sum(seg_real)}")
+    k_pad = sum(seg_pad)
+    wp = np.zeros([k_pad, n_pad], np.float32)
+    src = dst = 0
+    for real, pad in zip(seg_real, seg_pad):
+      wp[dst:dst + real, :n_real] = w[src:src + real]
+      src += real
+      dst += pad
+    nbytes = self._lib.gcb_packed_weight_bytes(k_pad, n_pad)
+    img = np.empty([nbytes], np.uint8)
+    _native.check(self._lib.gcb_pack_weight_host(
+        wp.ctypes.data, k_pad, n_pad, k_pad, n_pad, img.ctypes.data), "gcb_pack_weight_host")
+    return self._dev(img, torch.uint8), self._dev(wp, torch.float32), k_pad
+
+  def _make_mlp(self, params, stem: str, seg_real, seg_pad, n1_real: int,
+                layer_norm: bool) -> _native.Mlp:
+    def get(name, field):
+      try:
+        return np.asarray(params[name][field], np.float32)
+      except KeyError as e:
+        raise KeyError(f"missing parameter {name}:{field}") from e
+    if f"{stem}_mlp/~/linear_2" in params:
+      raise ValueError("only hidden_layers=1 MLPs are supported")
+    w0, b0 = get(f"{stem}_mlp/~/linear_0", "w"), get(f"{stem}_mlp/~/linear_0", "b")
+    w1, b1 = get(f"{stem}_mlp/~/linear_1", "w"), get(f"{stem}_mlp/~/linear_1", "b")
+    if w0.shape[1] != LATENT or w1.shape[0] != LATENT:
+      raise ValueError(f"{stem}: only latent/hidden size {LATENT} is supported")
+    if w1.shape[1] != n1_real:
+      raise ValueError(f"{stem}: output width {w1.shape[1]} != expected {n1_real}")
+    n1_pad = 512 if n1_real > 256 else 256
+    if n1_real == LATENT:
+      n1_pad = 512
+    mlp = _native.Mlp()
+    img0, f0, k0 = self._pack_linear(w0, seg_real, seg_pad, LATENT)
+    img1, f1, _ = self._pack_linear(w1, [LATENT], [LATENT], n1_pad)
+    pad = lambda v, n: np.concatenate([v, np.zeros([n - v.shape[0]], np.float32)])
+    mlp.w0_packed, mlp.w0_f32 = self._ptr(img0), self._ptr(f0)
+    mlp.b0 = self._ptr(self._dev(b0, torch.float32))
+    mlp.w1_packed, mlp.w1_f32 = self._ptr(img1), self._ptr(f1)
+    mlp.b1 = self._ptr(self._dev(pad(b1, n1_pad), torch.float32))
+    if layer_norm:
+      mlp.ln_scale = self._ptr(self._dev(pad(get(f"{stem}_layer_norm", "scale"), n1_pad),
+                                         torch.float32))
+      mlp.ln_offset = self._ptr(self._dev(pad(get(f"{stem}_layer_norm", "offset"), n1_pad),
+                                          torch.float32))
+    mlp.k0, mlp.n1, mlp.n1_valid = k0, n1_pad, n1_real
+    return mlp
+
+  def _upload_weights(self, params) -> None:
+    m = self._model
+    D = LATENT
+    cin_real, cin_pad = self.c_in + 3, self.c_in_pad
+    mk = self._make_mlp
+    g = "grid2mesh_gnn"
+    m.enc_grid = mk(params, mlp_stem(g, "encoder_nodes_", "grid_nodes"), [cin_real], [cin_pad], D, True)
+    m.enc_mesh = mk(params, mlp_stem(g, "encoder_nodes_", "mesh_nodes"), [cin_real], [cin_pad], D, True)
+    m.enc_e_g2m = mk(params, mlp_stem(g, "encoder_edges_", "grid2mesh"), [4], [16], D, True)
+    m.proc_e_g2m = mk(params, mlp_stem(g, "processor_edges_0_", "grid2mesh"), [D] * 3, [D] * 3, D, True)
+    m.proc_n_mesh_g2m = mk(params, mlp_stem(g, "processor_nodes_0_", "mesh_nodes"), [D] * 2, [D] * 2, D, True)
+    m.proc_n_grid_g2m = mk(params, mlp_stem(g, "processor_nodes_0_", "grid_nodes"), [D], [D], D, True)
+    g = "mesh_gnn"
+    m.enc_e_mesh = mk(params, mlp_stem(g, "encoder_edges_", "mesh"), [4], [16], D, True)
+    for k in range(self.msg_steps):
+      m.proc_e_mesh[k] = mk(params, mlp_stem(g, f"processor_edges_{k}_", "mesh"), [D] * 3, [D] * 3, D, True)
+      m.proc_n_mesh[k] = mk(params, mlp_stem(g, f"processor_nodes_{k}_", "mesh_nodes"), [D] * 2, [D] * 2, D, True)
+    g = "mesh2grid_gnn"
+    m.enc_e_m2g = mk(params, mlp_stem(g, "encoder_edges_", "mesh2grid"), [4], [16], D, True)
+    m.proc_e_m2g = mk(params, mlp_stem(g, "processor_edges_0_", "mesh2grid"), [D] * 3, [D] * 3, D, True)
+    m.proc_n_grid_m2g = mk(params, mlp_stem(g, "processor_nodes_0_", "grid_nodes"), [D] * 2, [D] * 2, D, True)
+    m.dec_grid = mk(params, mlp_stem(g, "decoder_nodes_", "grid_nodes"), [D], [D], self.n_out, False)
+
+  # -- workspace ---------------------------------------------------------------------
+  def _alloc_workspace(self) -> None:
+    m = self._model
+    f = lambda rows, cols: torch.empty([max(rows, 1), cols], dtype=torch.float32, device=self.device)
+    max_rows = max(m.num_grid, m.num_mesh, m.e_g2m, m.e_mesh, m.e_m2g)
+    big_edges = max(m.e_g2m, m.e_m2g)
+    self.hidden = f(max_rows, LATENT)
+    self.edge_a, self.edge_b = f(big_edges, LATENT), f(big_edges, LATENT)
+    self.grid_lat, self.mesh_lat = f(m.num_grid, LATENT), f(m.num_mesh, LATENT)
+    self.mesh_agg = f(m.num_mesh, LATENT)
+    self.mesh_edge, self.mesh_msg = f(m.e_mesh, LATENT), f(m.e_mesh, LATENT)
+    self.grid_in = f(m.num_grid, self.c_in_pad)
+    self.grid_out = f(m.num_grid, 256)
+    m.hidden, m.edge_a, m.edge_b = self._ptr(self.hidden), self._ptr(self.edge_a), self._ptr(self.edge_b)
+    m.grid_lat, m.mesh_lat, m.mesh_agg = self._ptr(self.grid_lat), self._ptr(self.mesh_lat), self._ptr(self.mesh_agg)
+    m.mesh_edge, m.mesh_msg = self._ptr(self.mesh_edge), self._ptr(self.mesh_msg)
+
+  def workspace_bytes(self) -> int:
+    ts = [self.hidden, self.edge_a, self.edge_b, self.grid_lat, self.mesh_lat, self.mesh_agg,
+          self.mesh_edge, self.mesh_msg, self.grid_in, self.grid_out]
+    return sum(t.numel() * t.element_size() for t in ts)
+
+  # -- execution ---------------------------------------------------------------------
+  @staticmethod
+  def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+  def set_precision(self, precision: str) -> None:
+    self._model.precision = _native.PRECISIONS[precision]
+    self.precision = precision
+
+  def pack_inputs(self, planes: torch.Tensor, mean: Optional[torch.Tensor] = None,
+                  scale: Optional[torch.Tensor] = None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """planes [c_in, Ng] (device, fp32, contiguous) -> grid_in [Ng, c_in_pad]."""
+    if planes.shape != (self.c_in, self.num_grid) or planes.dtype != torch.float32 \
+        or not planes.is_contiguous() or planes.device != self.device:
+      raise ValueError(f"planes must be a contiguous fp32 [{self.c_in}, {self.num_grid}] "
+                       f"tensor on {self.device}")
+    out = self.grid_in if out is None else out
+    _native.check(self._lib.gcb_pack_grid_features(
+        planes.data_ptr(), self.c_in, self.num_grid, self._ptr(mean), self._ptr(scale),
+        self.grid_static.data_ptr(), 3, out.data_ptr(), self.c_in_pad, self._stream()),
+        "gcb_pack_grid_features")
+    return out
+
+  def step(self, grid_in: Optional[torch.Tensor] = None,
+           grid_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """grid_in [Ng, c_in_pad] -> grid_out [Ng, 256] (n_out valid columns)."""
+    grid_in = self.grid_in if grid_in is None else grid_in
+    grid_out = self.grid_out if grid_out is None else grid_out
+    n = C.c_int32(0)
+    _native.check(self._lib.gcb_forward(C.byref(self._model), grid_in.data_ptr(),
+                                        grid_out.data_ptr(), self._stream(), C.byref(n)),
+                  "gcb_forward")
+    self.launches_per_step = int(n.value)
+    return grid_out
+
+  def unpack_outputs(self, planes_out: torch.Tensor, grid_out: Optional[torch.Tensor] = None,
+                     scale: Optional[torch.Tensor] = None, offset: Optional[torch.Tensor] = None,
+                     add_planes: Optional[torch.Tensor] = None,
+                     add_plane_index: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """grid_out [Ng,256] -> planes_out [n_out, Ng] (optionally un-normalised +
+    residual-added, see gcb_unpack_grid_outputs)."""
+    grid_out = self.grid_out if grid_out is None else grid_out
+    if planes_out.shape != (self.n_out, self.num_grid) or not planes_out.is_contiguous():
+      raise ValueError("planes_out must be a contiguous [n_out, Ng] tensor")
+    _native.check(self._lib.gcb_unpack_grid_outputs(
+        grid_out.data_ptr(), 256, self.n_out, self.num_grid, self._ptr(scale), self._ptr(offset),
+        self._ptr(add_planes), self._ptr(add_plane_index), planes_out.data_ptr(), self._stream()),
+        "gcb_unpack_grid_outputs")
+    return planes_out
+
+  def forward_features(self, grid_features: torch.Tensor) -> torch.Tensor:
+    """Convenience for parity tests: grid_features [Ng, B, c_in] (the reference's
+    `_inputs_to_grid_node_features` layout) -> [Ng, B, n_out]."""
+    ng, batch, c = grid_features.shape
+    outs = []
+    for b in range(batch):
+      planes = grid_features[:, b, :].t().contiguous().to(self.device, torch.float32)
+      self.pack_inputs(planes)
+      self.step()
+      outs.append(self.grid_out[:, :self.n_out].clone())
+    return torch.stack(outs, dim=1)

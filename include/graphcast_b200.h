@@ -1,0 +1,213 @@
+/* graphcast_b200 -- C ABI of the B200-native GraphCast hot path.
+ *
+ * This is the drop-in boundary: a plain C interface (pointers and sizes, no
+ * torch / C++ types) over hand-written sm_100a CUDA kernels.  The reference is
+ * pure Python/JAX and has no FFI of its own; each entry point below names the
+ * reference function (file:line under /root/reference) whose work it replaces.
+ * The Python mirror (graphcast_b200/graphcast.py, rollout.py) binds these with
+ * ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer inside gcb_* structs is a DEVICE pointer unless stated;
+ *     buffers are owned by the caller (PyTorch allocations in the Python host);
+ *   - all functions take a CUDA stream (cudaStream_t passed as void*) and are
+ *     asynchronous with respect to the host; nothing here allocates or syncs;
+ *   - return value 0 = success; otherwise a negative gcb_status and
+ *     gcb_last_error() describes the failure (thread-local string);
+ *   - float tensors are fp32 row-major; node/edge feature tables are
+ *     [rows, ld] with ld a multiple of 4 (16-byte rows).
+ */
+#ifndef GRAPHCAST_B200_H_
+#define GRAPHCAST_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCB_ABI_VERSION 1
+
+typedef enum {
+  GCB_OK = 0,
+  GCB_ERR_INVALID = -1,  /* bad argument (shape, alignment, null pointer) */
+  GCB_ERR_CUDA = -2,     /* a CUDA runtime call / launch failed */
+  GCB_ERR_UNSUPPORTED = -3
+} gcb_status;
+
+/* Arithmetic of the dense MLP contractions.
+ *   BF16X3    : every fp32 operand is split x = hi + lo (two bf16), the product is
+ *               formed as hi*hi + hi*lo + lo*hi on tcgen05 tensor cores with fp32
+ *               accumulation in TMEM.  ~2^-17 relative operand error: this is the
+ *               parity mode (<= 1e-4 vs the fp32 oracle over a full step).
+ *   BF16      : single bf16 product (the numerics of the reference's
+ *               casting.Bfloat16Cast demo stack, utils/casting.py:31-65); fast,
+ *               does NOT meet the 1e-4 gate.
+ *   FP32_SIMT : fp32 FFMA on CUDA cores; slow validation arm for the tensor path. */
+typedef enum { GCB_PREC_BF16X3 = 0, GCB_PREC_BF16 = 1, GCB_PREC_FP32_SIMT = 2 } gcb_precision;
+
+typedef enum { GCB_ACT_NONE = 0, GCB_ACT_SWISH = 1 } gcb_activation;
+
+/* One K-segment of a layer input.  The logical input row r of the layer is the
+ * concatenation over segments of
+ *     sum_{j < fan} table[(idx ? idx[r] : r) * fan + j, 0:k_valid]   (zero padded to k)
+ * i.e. a gathered node/edge row (jax_gather, utils/typed_graph_net.py:124-125,
+ * 431-445) or, with fan > 1, a fixed fan-in segment sum of consecutive rows
+ * (jraph.segment_sum for the mesh2grid graph, typed_graph_net.py:535-537). */
+typedef struct {
+  const float* table;   /* [*, ld] fp32 */
+  const int32_t* idx;   /* [rows] gather index or NULL (identity) */
+  int32_t ld;           /* row stride in floats, multiple of 4 */
+  int32_t k;            /* padded width, multiple of 16 */
+  int32_t k_valid;      /* real width (<= k, multiple of 4) */
+  int32_t fan;          /* >= 1 */
+} gcb_segment;
+
+/* One fused linear layer over `rows` rows:
+ *     z   = concat(segments)                         [rows, K],  K = sum k
+ *     y   = act(z @ W + bias)                        [rows, n]
+ *     y   = LayerNorm(y) * ln_scale + ln_offset      (if ln_scale != NULL; eps 1e-5)
+ *     out_y[r] = y[r]                                (if out_y  != NULL)
+ *     out[r]   = (residual ? residual[r] : 0) + y[r] (if out    != NULL)
+ * Replaces one hk.Linear (+ jax.nn.swish | + hk.LayerNorm + residual add) of
+ * build_mlp_with_maybe_layer_norm (utils/legacy/deep_typed_graph_net.py:205-247),
+ * the concat of jraph.concatenated_args, and the residuals of _process_step
+ * (deep_typed_graph_net.py:380-389). */
+typedef struct {
+  int32_t rows;
+  int32_t n;            /* padded output width: 256 or 512 */
+  int32_t n_valid;      /* real output width (<= n); columns beyond are not stored */
+  int32_t nseg;         /* 1..3 */
+  gcb_segment seg[3];
+  const void* w_packed; /* bf16 hi/lo tile image made by gcb_pack_weight_* */
+  const float* w_f32;   /* [K, n] fp32 row-major (FP32_SIMT arm only) */
+  const float* bias;    /* [n] */
+  const float* ln_scale;  /* [n] or NULL */
+  const float* ln_offset; /* [n] or NULL (required iff ln_scale) */
+  int32_t act;          /* gcb_activation */
+  const float* residual; int32_t ld_res;
+  float* out;   int32_t ld_out;
+  float* out_y; int32_t ld_out_y;
+  int32_t precision;    /* gcb_precision */
+} gcb_layer_desc;
+
+int gcb_abi_version(void);
+const char* gcb_last_error(void);
+
+/* Number of resident SMs used for persistent grids on `device` (query helper). */
+int gcb_sm_count(int device);
+
+/* Bytes of the packed bf16 weight image for a [k, n] layer (k multiple of 16). */
+int64_t gcb_packed_weight_bytes(int32_t k, int32_t n);
+
+/* Host-side packing (pure CPU, no CUDA): fp32 W[k_rows, n_cols] (row-major, ld =
+ * n_cols) -> image for a layer of padded shape [k, n]; rows/cols beyond the real
+ * ones are zero.  `dst` has gcb_packed_weight_bytes(k, n) bytes. */
+int gcb_pack_weight_host(const float* w, int32_t k_rows, int32_t n_cols, int32_t k, int32_t n,
+                         void* dst);
+
+/* Launch one fused layer. */
+int gcb_layer_forward(const gcb_layer_desc* d, void* stream);
+
+/* out[i, :] = sum_{e in [row_ptr[i], row_ptr[i+1])} msg[e, :]   (width 512).
+ * Deterministic receiver-sorted segmented sum; replaces jraph.segment_sum as
+ * called from _node_update (utils/typed_graph_net.py:532-538). */
+int gcb_segment_sum(const float* msg, int32_t ld_msg, const int32_t* row_ptr, int32_t num_nodes,
+                    float* out, int32_t ld_out, int32_t width, void* stream);
+
+/* Channel packing, device side.  planes: [n_ch, n_nodes] (channel-major, i.e. the
+ * (batch-sliced) variables stacked in dataset_to_stacked order);  feats:
+ * [n_nodes, ld] with columns [0,n_ch) = (planes - mean) / scale (mean/scale per
+ * channel, NULL = identity), columns [n_ch, n_ch+n_static) = node_static, and
+ * zero padding up to ld.  Replaces _inputs_to_grid_node_features
+ * (weathernext1_graph/graphcast.py:680-699), the structural-feature concat of
+ * _run_grid2mesh_gnn (:561-568) and normalization.normalize
+ * (utils/normalization.py:29-48). */
+int gcb_pack_grid_features(const float* planes, int32_t n_ch, int64_t n_nodes,
+                           const float* mean, const float* scale,
+                           const float* node_static, int32_t n_static,
+                           float* feats, int32_t ld, void* stream);
+
+/* Inverse for the outputs: y [n_nodes, ld_y] -> planes_out [n_out, n_nodes] with
+ *   planes_out[c] = y[:, c] * scale[c] + offset[c] + (add_plane_index[c] >= 0 ?
+ *                   add_planes[add_plane_index[c]] : 0).
+ * Replaces _grid_node_outputs_to_prediction (graphcast.py:701-723) and
+ * InputsAndResiduals._unnormalize_prediction_and_add_input
+ * (utils/normalization.py:113-132).  scale/offset/add_* may be NULL. */
+int gcb_unpack_grid_outputs(const float* y, int32_t ld_y, int32_t n_out, int64_t n_nodes,
+                            const float* scale, const float* offset,
+                            const float* add_planes, const int32_t* add_plane_index,
+                            float* planes_out, void* stream);
+
+/* ---- whole-step orchestration -------------------------------------------------- */
+
+/* One two-layer MLP (+ optional LayerNorm) of the model. */
+typedef struct {
+  const void* w0_packed; const float* w0_f32; const float* b0;   /* [k0, 512] */
+  const void* w1_packed; const float* w1_f32; const float* b1;   /* [512, n1] */
+  const float* ln_scale; const float* ln_offset;                 /* [n1] or NULL */
+  int32_t k0;            /* padded K of layer 0 (sum of its segments) */
+  int32_t n1;            /* padded output width (256 or 512) */
+  int32_t n1_valid;
+} gcb_mlp;
+
+#define GCB_MAX_MSG_STEPS 64
+
+/* Everything one forward step needs.  Edge arrays are in EXECUTION order
+ * (receiver-sorted for grid2mesh and mesh; the reference's own order for
+ * mesh2grid, which is receiver-sorted with fan-in 3). */
+typedef struct {
+  int32_t num_grid, num_mesh;
+  int32_t e_g2m, e_mesh, e_m2g;
+  int32_t c_in_pad;       /* padded width of the packed input features (mult. of 16) */
+  int32_t c_in_valid;     /* real width incl. the 3 structural features (mult. of 4 pad ok) */
+  int32_t msg_steps;
+  int32_t precision;
+
+  /* static graph */
+  const int32_t* g2m_snd; const int32_t* g2m_rcv; const int32_t* g2m_row_ptr;
+  const float*   g2m_feat;   /* [e_g2m, 4] */
+  const int32_t* mesh_snd; const int32_t* mesh_rcv; const int32_t* mesh_row_ptr;
+  const float*   mesh_feat;  /* [e_mesh, 4] */
+  const int32_t* m2g_snd; const int32_t* m2g_rcv;
+  const float*   m2g_feat;   /* [e_m2g, 4] */
+  const float*   mesh_in;    /* [num_mesh, c_in_pad]: zeros + structural (graphcast.py:573-583) */
+
+  /* weights */
+  gcb_mlp enc_grid, enc_mesh, enc_e_g2m, proc_e_g2m, proc_n_mesh_g2m, proc_n_grid_g2m;
+  gcb_mlp enc_e_mesh;
+  gcb_mlp proc_e_mesh[GCB_MAX_MSG_STEPS];
+  gcb_mlp proc_n_mesh[GCB_MAX_MSG_STEPS];
+  gcb_mlp enc_e_m2g, proc_e_m2g, proc_n_grid_m2g, dec_grid;
+
+  /* workspace (fp32): */
+  float* hidden;      /* [max_rows, 512] */
+  float* edge_a;      /* [max(e_g2m,e_m2g), 512] */
+  float* edge_b;      /* [max(e_g2m,e_m2g), 512] */
+  float* grid_lat;    /* [num_grid, 512] latent grid nodes */
+  float* mesh_lat;    /* [num_mesh, 512] latent mesh nodes */
+  float* mesh_agg;    /* [num_mesh, 512] */
+  float* mesh_edge;   /* [e_mesh, 512] latent mesh edges */
+  float* mesh_msg;    /* [e_mesh, 512] */
+} gcb_model;
+
+/* One 6 h step for one batch element:
+ *   grid_in  [num_grid, c_in_pad]  (from gcb_pack_grid_features)
+ *   grid_out [num_grid, 256]       (columns [0, n_out) valid)
+ * Replaces GraphCast.__call__'s _run_grid2mesh_gnn / _run_mesh_gnn /
+ * _run_mesh2grid_gnn (weathernext1_graph/graphcast.py:309-323, 550-678) and the
+ * DeepTypedGraphNet / InteractionNetwork machinery under them
+ * (utils/legacy/deep_typed_graph_net.py:180-401, utils/typed_graph_net.py:272-546).
+ * `launches` (host pointer, may be NULL) receives the number of kernels launched. */
+int gcb_forward(const gcb_model* m, const float* grid_in, float* grid_out, void* stream,
+                int32_t* launches);
+
+/* Device self-test of the tensor-core layer against the FP32_SIMT arm on random
+ * data (used by tests and __graft_entry__.smoke); returns max |diff| / max |ref|
+ * through *rel_err.  Allocates its own scratch. */
+int gcb_selftest_layer(int32_t rows, int32_t k, int32_t n, int32_t precision, float* rel_err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAPHCAST_B200_H_ */

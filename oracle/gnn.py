@@ -1,0 +1,210 @@
+"""Oracle: GraphCast encode-process-decode forward on the CPU (torch-CPU tensors).
+
+TEST INFRASTRUCTURE -- see oracle/__init__.py.  PARITY UNPINNED (restatement,
+not executed reference).
+
+Restates, for explicit index arrays and a Haiku-named parameter dict:
+  * hk.nets.MLP + hk.LayerNorm + jraph.concatenated_args as wired by
+    `build_mlp_with_maybe_layer_norm`  (utils/legacy/deep_typed_graph_net.py:205-247)
+  * GraphMapFeatures embedders / decoder (utils/typed_graph_net.py:657-696,
+    deep_typed_graph_net.py:250-271, 314-322)
+  * InteractionNetwork step: gather senders/receivers, edge fn on
+    concat[edge, sender, receiver] (typed_graph_net.py:369-484, 637-638),
+    segment_sum over receivers and node fn on concat[node, agg]
+    (typed_graph_net.py:487-546, 646-647), node and edge residuals
+    (deep_typed_graph_net.py:372-393)
+  * the three GNN calls and their glue (weathernext1_graph/graphcast.py:550-678).
+
+Third-party arithmetic restated from its published definition (packages are not
+in /root/reference; versions unpinned in its setup.py:37,43):
+  hk.Linear      y = x @ w + b, w:[in,out]
+  hk.nets.MLP    activation between layers, none after the last
+  hk.LayerNorm   axis=-1, eps=1e-5: (x-mean)*rsqrt(var_biased+eps)*scale+offset
+  jax.nn.swish   x*sigmoid(x)
+  jraph.segment_sum  sum of rows per segment id
+"""
+
+from __future__ import annotations
+
+from typing import Dict, Mapping, Optional
+
+import numpy as np
+import torch
+
+Params = Dict[str, Dict[str, np.ndarray]]
+
+
+def mlp_name(gnn: str, prefix: str, set_name: str) -> str:
+  """Haiku module path stem (deep_typed_graph_net.py:205-208,251-262,295-307,
+  315-319; gnn names graphcast.py:217,233,261)."""
+  return f"{gnn}/~_networks_builder/{prefix}{set_name}"
+
+
+def swish(x: torch.Tensor) -> torch.Tensor:
+  return x * torch.sigmoid(x)
+
+
+def layer_norm(x, scale, offset, eps: float = 1e-5):
+  mean = x.mean(dim=-1, keepdim=True)
+  var = ((x - mean) ** 2).mean(dim=-1, keepdim=True)       # biased
+  return (x - mean) * torch.rsqrt(var + eps) * scale + offset
+
+
+class Oracle:
+  """Holds params as torch-CPU tensors of one dtype and runs the forward."""
+
+  def __init__(self, params: Params, dtype=torch.float32):
+    self.dtype = dtype
+    self.p = {k: {n: torch.as_tensor(np.asarray(a)).to(dtype) for n, a in v.items()}
+              for k, v in params.items()}
+
+  def matmul(self, x, w):
+    """x @ w.  Hook so tests can emulate reduced-precision tensor-core products."""
+    return x @ w
+
+  # hk.nets.MLP (+ optional hk.LayerNorm) on the concatenation of `args`.
+  def mlp(self, stem: str, args, use_layer_norm: bool = True):
+    x = torch.cat(list(args), dim=-1)
+    i = 0
+    while f"{stem}_mlp/~/linear_{i}" in self.p:
+      lin = self.p[f"{stem}_mlp/~/linear_{i}"]
+      if i > 0:
+        x = swish(x)
+      x = self.matmul(x, lin["w"]) + lin["b"]
+      i += 1
+    if use_layer_norm:
+      ln = self.p[f"{stem}_layer_norm"]
+      x = layer_norm(x, ln["scale"], ln["offset"])
+    return x
+
+  @staticmethod
+  def segment_sum(data, segment_ids, num_segments):
+    out = torch.zeros((num_segments,) + tuple(data.shape[1:]), dtype=data.dtype)
+    out.index_add_(0, segment_ids, data)
+    return out
+
+  def forward(self, graph: Mapping[str, np.ndarray], grid_features: np.ndarray,
+              return_intermediates: bool = False):
+    """One step.  grid_features [Ng, B, C_in] (already normalised + packed).
+
+    graph keys: grid_node_feats [Ng,3], mesh_node_feats [Nm,3],
+      g2m_senders/g2m_receivers [E1], g2m_edge_feats [E1,4],
+      mesh_senders/mesh_receivers [E2], mesh_edge_feats [E2,4],
+      m2g_senders/m2g_receivers [E3], m2g_edge_feats [E3,4].
+    Returns [Ng, B, n_out].
+    """
+    t = lambda a: torch.as_tensor(np.asarray(a)).to(self.dtype)
+    idx = lambda a: torch.as_tensor(np.asarray(a)).to(torch.int64)
+    X = t(grid_features)
+    n_grid, batch, _ = X.shape
+    bcast = lambda f: t(f)[:, None, :].expand(-1, batch, -1)   # _add_batch_second_axis :726-730
+    inter = {}
+
+    # ---- grid2mesh_gnn (graphcast.py:550-604) ----
+    sg, sm = bcast(graph["grid_node_feats"]), bcast(graph["mesh_node_feats"])
+    n_mesh = sm.shape[0]
+    grid_in = torch.cat([X, sg], dim=-1)
+    mesh_in = torch.cat([torch.zeros((n_mesh,) + tuple(X.shape[1:]), dtype=self.dtype), sm],
+                        dim=-1)                                 # :573-583
+    g = "grid2mesh_gnn"
+    vg0 = self.mlp(mlp_name(g, "encoder_nodes_", "grid_nodes"), [grid_in])
+    vm0 = self.mlp(mlp_name(g, "encoder_nodes_", "mesh_nodes"), [mesh_in])
+    e1 = self.mlp(mlp_name(g, "encoder_edges_", "grid2mesh"), [bcast(graph["g2m_edge_feats"])])
+    s1, r1 = idx(graph["g2m_senders"]), idx(graph["g2m_receivers"])
+    m1 = self.mlp(mlp_name(g, "processor_edges_0_", "grid2mesh"), [e1, vg0[s1], vm0[r1]])
+    agg1 = self.segment_sum(m1, r1, n_mesh)        # f32_aggregation is a no-op in f32
+    vm1 = vm0 + self.mlp(mlp_name(g, "processor_nodes_0_", "mesh_nodes"), [vm0, agg1])
+    vg1 = vg0 + self.mlp(mlp_name(g, "processor_nodes_0_", "grid_nodes"), [vg0])
+    if return_intermediates:
+      inter.update(vg0=vg0, vm0=vm0, e1=e1, m1=m1, agg1=agg1, vm1=vm1, vg1=vg1)
+
+    # ---- mesh_gnn (graphcast.py:606-639) ----
+    g = "mesh_gnn"
+    e = self.mlp(mlp_name(g, "encoder_edges_", "mesh"), [bcast(graph["mesh_edge_feats"])])
+    s2, r2 = idx(graph["mesh_senders"]), idx(graph["mesh_receivers"])
+    v = vm1
+    k = 0
+    while mlp_name(g, f"processor_edges_{k}_", "mesh") + "_mlp/~/linear_0" in self.p:
+      m = self.mlp(mlp_name(g, f"processor_edges_{k}_", "mesh"), [e, v[s2], v[r2]])
+      agg = self.segment_sum(m, r2, n_mesh)
+      v_new = v + self.mlp(mlp_name(g, f"processor_nodes_{k}_", "mesh_nodes"), [v, agg])
+      e = e + m
+      v = v_new
+      k += 1
+    if return_intermediates:
+      inter.update(v_mesh=v, e_mesh=e)
+
+    # ---- mesh2grid_gnn (graphcast.py:641-678) ----
+    g = "mesh2grid_gnn"
+    e3 = self.mlp(mlp_name(g, "encoder_edges_", "mesh2grid"), [bcast(graph["m2g_edge_feats"])])
+    s3, r3 = idx(graph["m2g_senders"]), idx(graph["m2g_receivers"])
+    m3 = self.mlp(mlp_name(g, "processor_edges_0_", "mesh2grid"), [e3, v[s3], vg1[r3]])
+    agg3 = self.segment_sum(m3, r3, n_grid)
+    vg2 = vg1 + self.mlp(mlp_name(g, "processor_nodes_0_", "grid_nodes"), [vg1, agg3])
+    out = self.mlp(mlp_name(g, "decoder_nodes_", "grid_nodes"), [vg2], use_layer_norm=False)
+    if return_intermediates:
+      inter.update(vg2=vg2)
+      return out, inter
+    return out
+
+
+def truncated_normal(rng: np.random.Generator, shape, stddev: float) -> np.ndarray:
+  """hk.initializers.TruncatedNormal: N(0,1) truncated to [-2,2], times stddev."""
+  x = rng.standard_normal(shape)
+  bad = np.abs(x) > 2.0
+  while bad.any():
+    x[bad] = rng.standard_normal(int(bad.sum()))
+    bad = np.abs(x) > 2.0
+  return (x * stddev).astype(np.float32)
+
+
+def init_params(*, c_in: int, n_out: int, latent: int = 512, msg_steps: int = 16,
+                hidden_layers: int = 1, seed: int = 1, randomize_affine: bool = False
+                ) -> Params:
+  """Haiku-default initialisation of every GraphCast parameter:
+  w ~ TruncNormal(1/sqrt(fan_in)), b = 0, LN scale = 1, offset = 0.
+  `randomize_affine` perturbs b / scale / offset so tests exercise those terms.
+  Shapes follow deep_typed_graph_net.py:205-322 with the concat orders of
+  typed_graph_net.py:637-647."""
+  rng = np.random.default_rng(seed)
+  params: Params = {}
+
+  def add_mlp(gnn, prefix, set_name, d_in, d_out, layer_norm=True):
+    stem = mlp_name(gnn, prefix, set_name)
+    sizes = [latent] * hidden_layers + [d_out]
+    fan_in = d_in
+    for i, size in enumerate(sizes):
+      w = truncated_normal(rng, (fan_in, size), 1.0 / np.sqrt(fan_in))
+      b = np.zeros([size], np.float32)
+      if randomize_affine:
+        b = (0.1 * rng.standard_normal(size)).astype(np.float32)
+      params[f"{stem}_mlp/~/linear_{i}"] = {"w": w, "b": b}
+      fan_in = size
+    if layer_norm:
+      scale = np.ones([d_out], np.float32)
+      offset = np.zeros([d_out], np.float32)
+      if randomize_affine:
+        scale = (1.0 + 0.1 * rng.standard_normal(d_out)).astype(np.float32)
+        offset = (0.1 * rng.standard_normal(d_out)).astype(np.float32)
+      params[f"{stem}_layer_norm"] = {"scale": scale, "offset": offset}
+
+  D = latent
+  g = "grid2mesh_gnn"
+  add_mlp(g, "encoder_nodes_", "grid_nodes", c_in + 3, D)
+  add_mlp(g, "encoder_nodes_", "mesh_nodes", c_in + 3, D)
+  add_mlp(g, "encoder_edges_", "grid2mesh", 4, D)
+  add_mlp(g, "processor_edges_0_", "grid2mesh", 3 * D, D)
+  add_mlp(g, "processor_nodes_0_", "grid_nodes", D, D)
+  add_mlp(g, "processor_nodes_0_", "mesh_nodes", 2 * D, D)
+  g = "mesh_gnn"
+  add_mlp(g, "encoder_edges_", "mesh", 4, D)
+  for k in range(msg_steps):
+    add_mlp(g, f"processor_edges_{k}_", "mesh", 3 * D, D)
+    add_mlp(g, f"processor_nodes_{k}_", "mesh_nodes", 2 * D, D)
+  g = "mesh2grid_gnn"
+  add_mlp(g, "encoder_edges_", "mesh2grid", 4, D)
+  add_mlp(g, "processor_edges_0_", "mesh2grid", 3 * D, D)
+  add_mlp(g, "processor_nodes_0_", "grid_nodes", 2 * D, D)
+  add_mlp(g, "processor_nodes_0_", "mesh_nodes", D, D)       # traced but dead
+  add_mlp(g, "decoder_nodes_", "grid_nodes", D, n_out, layer_norm=False)
+  return params
