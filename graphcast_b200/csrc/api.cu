@@ -64,6 +64,44 @@ int sm_count_cached() {
   return cached[dev];
 }
 
+// ---- optional per-launch profiling (CUDA events on the launching stream) ----------
+struct ProfRec {
+  cudaEvent_t beg, end;
+  int kind;
+  double flops, bytes;
+};
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_event_pool;
+
+cudaEvent_t pool_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct ProfScope {
+  bool on;
+  cudaStream_t st;
+  ProfRec rec;
+  ProfScope(cudaStream_t s, int kind, double flops, double bytes) : on(g_prof_on), st(s) {
+    if (!on) return;
+    rec.kind = kind; rec.flops = flops; rec.bytes = bytes;
+    rec.beg = pool_event(); rec.end = pool_event();
+    cudaEventRecord(rec.beg, st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(rec.end, st);
+    g_prof.push_back(rec);
+  }
+};
+
 int validate_layer(const gcb_layer_desc* d) {
   GCB_CHECK_ARG(d != nullptr, "null descriptor");
   GCB_CHECK_ARG(d->rows >= 0, "rows < 0");
@@ -227,6 +265,18 @@ int gcb_layer_forward(const gcb_layer_desc* d, void* stream) {
   if (rc) return rc;
   if (d->rows == 0) return GCB_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double kv = 0, a_elems = 0;
+  for (int i = 0; i < d->nseg; ++i) {
+    kv += d->seg[i].k_valid;
+    a_elems += static_cast<double>(d->seg[i].k_valid) * d->seg[i].fan;
+  }
+  const double rows = d->rows;
+  const double flops = 2.0 * rows * kv * d->n_valid;
+  const double bytes = 4.0 * (rows * a_elems + kv * d->n_valid +
+                              rows * d->n_valid * ((d->out ? 1 : 0) + (d->out_y ? 1 : 0) +
+                                                   (d->residual ? 1 : 0)));
+  ProfScope prof(st, d->precision == GCB_PREC_FP32_SIMT ? GCB_KIND_LAYER_SIMT : GCB_KIND_LAYER_TC,
+                 flops, bytes);
   switch (d->precision) {
     case GCB_PREC_BF16X3: return launch_tc<true>(*d, st);
     case GCB_PREC_BF16: return launch_tc<false>(*d, st);
@@ -244,6 +294,8 @@ int gcb_segment_sum(const float* msg, int32_t ld_msg, const int32_t* row_ptr, in
   long long blocks = (static_cast<long long>(num_nodes) + warps_per_block - 1) / warps_per_block;
   const long long cap = static_cast<long long>(sm_count_cached()) * 16;
   if (blocks > cap) blocks = cap;
+  ProfScope prof(static_cast<cudaStream_t>(stream), GCB_KIND_SEGMENT_SUM, 0.0,
+                 4.0 * width * (static_cast<double>(num_nodes) + 0.0) + 0.0);
   gcb::segment_sum_kernel<4><<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       msg, ld_msg, row_ptr, num_nodes, out, ld_out);
   GCB_CUDA(cudaGetLastError());
@@ -258,6 +310,8 @@ int gcb_pack_grid_features(const float* planes, int32_t n_ch, int64_t n_nodes, c
   GCB_CHECK_ARG(n_static == 0 || node_static != nullptr, "node_static is null");
   if (n_nodes == 0) return GCB_OK;
   dim3 grid(static_cast<unsigned>((n_nodes + 31) / 32), static_cast<unsigned>((ld + 31) / 32));
+  ProfScope prof(static_cast<cudaStream_t>(stream), GCB_KIND_PACK, 0.0,
+                 4.0 * n_nodes * (static_cast<double>(n_ch) + n_static + ld));
   gcb::pack_grid_features_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       planes, n_ch, n_nodes, mean, scale, node_static, n_static, feats, ld);
   GCB_CUDA(cudaGetLastError());
@@ -272,6 +326,8 @@ int gcb_unpack_grid_outputs(const float* y, int32_t ld_y, int32_t n_out, int64_t
   GCB_CHECK_ARG((add_planes == nullptr) == (add_plane_index == nullptr), "add_planes/index mismatch");
   if (n_nodes == 0) return GCB_OK;
   dim3 grid(static_cast<unsigned>((n_nodes + 31) / 32), static_cast<unsigned>((n_out + 31) / 32));
+  ProfScope prof(static_cast<cudaStream_t>(stream), GCB_KIND_UNPACK, 0.0,
+                 4.0 * n_nodes * n_out * (add_planes ? 3.0 : 2.0));
   gcb::unpack_grid_outputs_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       y, ld_y, n_out, n_nodes, scale, offset, add_planes, add_plane_index, planes_out);
   GCB_CUDA(cudaGetLastError());
@@ -351,6 +407,33 @@ int gcb_forward(const gcb_model* m, const float* grid_in, float* grid_out, void*
   if ((rc = run_mlp(c, m->dec_grid, m->num_grid, 1, s, nullptr, grid_out, 256, nullptr))) return rc;
 
   if (launches) *launches = c.launches;
+  return GCB_OK;
+}
+
+int gcb_profile_begin(void) {
+  for (auto& r : g_prof) { g_event_pool.push_back(r.beg); g_event_pool.push_back(r.end); }
+  g_prof.clear();
+  g_prof_on = true;
+  return GCB_OK;
+}
+
+int gcb_profile_end(int32_t capacity, int32_t* kinds, float* ms, double* flops, double* bytes,
+                    int32_t* count) {
+  g_prof_on = false;
+  GCB_CHECK_ARG(count != nullptr, "count is null");
+  const int n = static_cast<int>(g_prof.size());
+  *count = n;
+  for (int i = 0; i < n && i < capacity; ++i) {
+    GCB_CUDA(cudaEventSynchronize(g_prof[i].end));
+    float t = 0.f;
+    GCB_CUDA(cudaEventElapsedTime(&t, g_prof[i].beg, g_prof[i].end));
+    if (kinds) kinds[i] = g_prof[i].kind;
+    if (ms) ms[i] = t;
+    if (flops) flops[i] = g_prof[i].flops;
+    if (bytes) bytes[i] = g_prof[i].bytes;
+  }
+  for (auto& r : g_prof) { g_event_pool.push_back(r.beg); g_event_pool.push_back(r.end); }
+  g_prof.clear();
   return GCB_OK;
 }
 

@@ -133,7 +133,8 @@ def cached_static_graph(*, grid_lat: np.ndarray, grid_lon: np.ndarray,
   if cache_dir is None:
     cache_dir = os.environ.get(
         "GRAPHCAST_B200_CACHE",
-        os.path.join(os.path.dirname(os.path.abspath(__file__)), "_cache"))
+        os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                     ".graph_cache"))
   h = hashlib.sha1()
   h.update(np.ascontiguousarray(grid_lat, dtype=np.float32).tobytes())
   h.update(np.ascontiguousarray(grid_lon, dtype=np.float32).tobytes())

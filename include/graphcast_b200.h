@@ -202,6 +202,21 @@ typedef struct {
 int gcb_forward(const gcb_model* m, const float* grid_in, float* grid_out, void* stream,
                 int32_t* launches);
 
+/* Per-launch profiling.  Between gcb_profile_begin() and gcb_profile_end() every
+ * kernel launched through this ABI is bracketed by CUDA events on its stream.
+ * gcb_profile_end synchronises them and returns, per launch (in launch order,
+ * at most `capacity` entries; *count = total launches): its kind, duration in ms,
+ * and its ALGORITHMIC flops / HBM bytes (layer: 2*rows*K*n flops; inputs incl.
+ * gathers + weights + outputs bytes.  segment sum reports only the output
+ * bytes -- the caller adds edges*width*4).  Not thread safe. */
+typedef enum {
+  GCB_KIND_LAYER_TC = 0, GCB_KIND_SEGMENT_SUM = 1, GCB_KIND_PACK = 2, GCB_KIND_UNPACK = 3,
+  GCB_KIND_LAYER_SIMT = 4
+} gcb_kernel_kind;
+int gcb_profile_begin(void);
+int gcb_profile_end(int32_t capacity, int32_t* kinds, float* ms, double* flops, double* bytes,
+                    int32_t* count);
+
 /* Device self-test of the tensor-core layer against the FP32_SIMT arm on random
  * data (used by tests and __graft_entry__.smoke); returns max |diff| / max |ref|
  * through *rel_err.  Allocates its own scratch. */
