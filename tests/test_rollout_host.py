@@ -1,0 +1,89 @@
+"""Rollout driver host logic (no GPU): chunking, relative time coordinates,
+next-input assembly (reference rollout.py:437-445, 453-457, 581-604) with a CPU
+stand-in predictor, checked against a direct restatement."""
+import numpy as np
+import pytest
+
+from graphcast_b200 import graphcast, rollout, synthetic
+from graphcast_b200 import xarray_shim as xs
+
+
+class PersistencePlusOne(graphcast.Predictor):
+  """prediction = last input frame + 1 for every target (template decides names)."""
+
+  def __init__(self):
+    self.seen_times = []
+
+  def __call__(self, inputs, targets_template, forcings, **kw):
+    self.seen_times.append((tuple(inputs.coords["time"][1]), tuple(targets_template.coords["time"][1])))
+    out = xs.Dataset(coords=targets_template.coords)
+    for name, t in targets_template.data_vars.items():
+      if name in inputs:
+        last = inputs[name].isel(time=slice(-1, None))
+        out[name] = xs.DataArray(np.asarray(last.values) + 1.0, last.dims).transpose(*t.dims)
+      else:
+        out[name] = xs.DataArray(np.full(t.shape, 5.0, np.float32), t.dims)
+    return out
+
+
+def _example(steps):
+  inputs, template, forcings = synthetic.make_example(graphcast.TASK_13_PRECIP_OUT, 30.0,
+                                                      num_target_steps=steps, seed=3)
+  return inputs, template, forcings
+
+
+def test_chunked_prediction_matches_direct_recursion():
+  inputs, template, forcings = _example(4)
+  pred = PersistencePlusOne()
+  out = rollout.chunked_prediction(lambda rng, **kw: pred(**kw), rng=None, inputs=inputs,
+                                   targets_template=template, forcings=forcings)
+  assert out.sizes["time"] == 4
+  np.testing.assert_array_equal(out.coords["time"][1], template.coords["time"][1])
+  t0 = inputs.data_vars["2m_temperature"].values[:, -1]
+  for k in range(4):
+    np.testing.assert_allclose(out.data_vars["2m_temperature"].values[:, k], t0 + (k + 1), rtol=1e-6)
+  # precipitation is a target but not an input in TASK_13_PRECIP_OUT -> predicted directly
+  assert np.all(out.data_vars["total_precipitation_6hr"].values == 5.0)
+  # every call saw the time coordinates of the first chunk (relative times)
+  assert len(set(pred.seen_times)) == 1
+
+
+def test_next_inputs_keep_last_two_frames_and_forcings():
+  inputs, template, forcings = _example(2)
+  frame = PersistencePlusOne()(inputs, template.isel(time=slice(0, 1)), None)
+  nxt = rollout._get_next_inputs(inputs, frame.assign(forcings.isel(time=slice(0, 1))))
+  assert set(nxt.keys()) == set(inputs.keys())
+  g_prev = inputs.data_vars["geopotential"].values
+  g_next = nxt.data_vars["geopotential"].values
+  np.testing.assert_array_equal(g_next[:, 0], g_prev[:, 1])
+  np.testing.assert_array_equal(g_next[:, 1], g_prev[:, 1] + 1.0)
+  np.testing.assert_array_equal(nxt.data_vars["toa_incident_solar_radiation"].values[:, 1],
+                                forcings.data_vars["toa_incident_solar_radiation"].values[:, 0])
+  np.testing.assert_array_equal(nxt.data_vars["land_sea_mask"].values,
+                                inputs.data_vars["land_sea_mask"].values)
+
+
+def test_errors():
+  inputs, template, forcings = _example(3)
+  fn = lambda rng, **kw: PersistencePlusOne()(**kw)
+  with pytest.raises(ValueError, match="evenly divide"):
+    rollout.chunked_prediction(fn, None, inputs, template, forcings, num_steps_per_chunk=2)
+  bad = template.assign_coords(time=np.array([6, 12, 24]) * np.timedelta64(1, "h"))
+  with pytest.raises(ValueError, match="evenly spaced"):
+    rollout.chunked_prediction(fn, None, inputs, bad, forcings)
+  with pytest.raises(ValueError, match="replica_axis"):
+    list(rollout.chunked_prediction_generator(fn, None, inputs, template, 1, forcings,
+                                              pmap_devices=[0]))
+  # an input with a time axis that is neither predicted nor forced
+  inputs2 = inputs.copy()
+  inputs2["mystery"] = inputs.data_vars["2m_temperature"]
+  with pytest.raises(ValueError, match="not predicted or forced"):
+    rollout.chunked_prediction(fn, None, inputs2, template, forcings)
+
+
+def test_extend_targets_template():
+  _, template, _ = _example(1)
+  ext = rollout.extend_targets_template(template, 40)
+  assert ext.sizes["time"] == 40
+  assert ext.coords["time"][1][-1] == np.timedelta64(240, "h")
+  assert ext.data_vars["temperature"].shape[1] == 40
