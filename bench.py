@@ -224,6 +224,8 @@ def run_b200(args):
   torch.cuda.set_device(local)
   dev = torch.device(f"cuda:{local}")
   lib = _native.lib()
+  if args.cluster:
+    _native.check(lib.gcb_set_cluster_size(args.cluster), "gcb_set_cluster_size")
 
   res, mesh, task_name = WORKLOADS[args.workload]
   task = getattr(graphcast, task_name)
@@ -360,7 +362,7 @@ def run_b200(args):
         "data": "synthetic",
         "config": {"workload": args.workload, "resolution_deg": res, "mesh_size": mesh,
                    "levels": len(task.pressure_levels), "latent": 512, "msg_steps": 16,
-                   "batch": 1, "precision": args.precision,
+                   "batch": 1, "precision": args.precision, "cluster": args.cluster or "default(2)",
                    "parallelism": "1 forecast per GPU (ensemble members), no collective",
                    "l2_policy": "working set per step (>20 GB) far exceeds the 126 MB L2; no flush needed",
                    "setup_s": setup_s},
@@ -389,6 +391,7 @@ def main():
                   default="graphcast_small_1deg_13lvl")
   ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=5)
   ap.add_argument("--skip-cpu-baseline", action="store_true")
+  ap.add_argument("--cluster", type=int, default=0, help="CTAs per cluster (0 = library default)")
   args = ap.parse_args()
   if args.impl == "reference":
     run_reference(args)

@@ -80,6 +80,7 @@ EXPORTS = {
     "gcb_unpack_grid_outputs": (C.c_int, [_fp, C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp,
                                           _fp, _fp, _fp]),
     "gcb_forward": (C.c_int, [C.POINTER(Model), _fp, _fp, _fp, C.POINTER(C.c_int32)]),
+    "gcb_set_cluster_size": (C.c_int, [C.c_int32]),
     "gcb_profile_begin": (C.c_int, []),
     "gcb_profile_end": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.POINTER(C.c_int32)]),
     "gcb_selftest_layer": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32,

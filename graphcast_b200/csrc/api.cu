@@ -136,21 +136,46 @@ int validate_layer(const gcb_layer_desc* d) {
   return GCB_OK;
 }
 
+int g_cluster_size = 2;   // CTAs per cluster sharing the weight stream (1, 2 or 4)
+
 template <bool kSplit>
 int launch_tc(const gcb_layer_desc& d, cudaStream_t stream) {
   using Cfg = gcb::TcConfig<kSplit>;
   static bool attr_set[64] = {false};
+  static int max_clusters[64][5] = {{0}};
   int dev = 0;
   GCB_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+  GCB_CHECK_ARG(dev >= 0 && dev < 64, "device index out of range");
+  if (!attr_set[dev]) {
     GCB_CUDA(cudaFuncSetAttribute(gcb::mlp_layer_tc_kernel<kSplit>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set[dev] = true;
   }
+  const int csize = g_cluster_size;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(gcb::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters[dev][csize] == 0) {
+    cfg.gridDim = dim3(sm_count_cached() / csize * csize);
+    int nc = 0;
+    GCB_CUDA(cudaOccupancyMaxActiveClusters(&nc, gcb::mlp_layer_tc_kernel<kSplit>, &cfg));
+    if (nc <= 0) return fail(GCB_ERR_CUDA, "no resident cluster fits on this device");
+    max_clusters[dev][csize] = nc;
+  }
   const int tiles = (d.rows + gcb::kTileM - 1) / gcb::kTileM;
-  const int grid = tiles < sm_count_cached() ? tiles : sm_count_cached();
-  gcb::mlp_layer_tc_kernel<kSplit><<<grid, gcb::kThreads, Cfg::kSmemBytes, stream>>>(d);
-  GCB_CUDA(cudaGetLastError());
+  int clusters = (tiles + csize - 1) / csize;
+  if (clusters > max_clusters[dev][csize]) clusters = max_clusters[dev][csize];
+  cfg.gridDim = dim3(clusters * csize);
+  GCB_CUDA(cudaLaunchKernelEx(&cfg, gcb::mlp_layer_tc_kernel<kSplit>, d));
   return GCB_OK;
 }
 
@@ -407,6 +432,12 @@ int gcb_forward(const gcb_model* m, const float* grid_in, float* grid_out, void*
   if ((rc = run_mlp(c, m->dec_grid, m->num_grid, 1, s, nullptr, grid_out, 256, nullptr))) return rc;
 
   if (launches) *launches = c.launches;
+  return GCB_OK;
+}
+
+int gcb_set_cluster_size(int32_t ctas) {
+  GCB_CHECK_ARG(ctas == 1 || ctas == 2 || ctas == 4, "cluster size must be 1, 2 or 4");
+  g_cluster_size = ctas;
   return GCB_OK;
 }
 

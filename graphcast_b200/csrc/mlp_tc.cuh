@@ -2,17 +2,21 @@
 //
 //   out[r] = residual[r] + LN( act( concat_s gather_s(r) @ W + bias ) )
 //
-// One persistent CTA per SM processes 128-row tiles.  Warp roles:
-//   warp 0        weight producer: one lane streams the pre-packed bf16 weight
-//                 image of each K-step into shared memory with cp.async.bulk
-//                 (TMA engine), completing on the stage's mbarrier.
+// One persistent CTA per SM processes 128-row tiles; the CTAs of a thread-block
+// cluster process consecutive tiles in lockstep and share the weight stream.
+// Warp roles:
+//   warp 0        weight producer: one lane streams 1/cluster of the pre-packed bf16
+//                 weight image of each K-step with cp.async.bulk (TMA engine),
+//                 multicast to every CTA of the cluster, completing on each CTA's
+//                 stage mbarrier (cuts L2->SM weight traffic by the cluster size).
 //   warp 1        MMA issuer: one lane issues tcgen05.mma (M=128, N=256 x n/256,
 //                 K=16) per stage -- three products per stage in BF16X3 mode
 //                 (hi*hi, hi*lo, lo*hi) -- accumulating fp32 in TMEM; commits
 //                 free the stage and finally publish the accumulator.
 //   warp 2        TMEM allocator (512 columns = 128 x 512 fp32 accumulator).
 //   warps 4-7     epilogue: tcgen05.ld the accumulator (thread = row), bias,
-//                 swish | LayerNorm (+ residual), vectorised global stores.
+//                 swish | LayerNorm (+ residual); 32x32 blocks are transposed through
+//                 shared memory so global stores / residual loads are full 128 B lines.
 //   warps 8-15    activation producers (two groups of four warps, alternating
 //                 K-steps): gather the fp32 rows of every K-segment through the
 //                 sender / receiver index (ld.global.v4), split to bf16 hi/lo and
@@ -22,8 +26,9 @@
 //
 // Shared-memory operand layout (no swizzle, K-major): a [R x 16] bf16 operand of
 // one K-step is two "K chunks" of 8 elements; chunk c, row r lives at byte
-// c * (R*16) + r*16.  Eight consecutive rows form one 128-byte core matrix,
-// so SBO = 128 and LBO = R*16 (see ptx.cuh make_smem_desc).
+// c * LBO + r*16.  Eight consecutive rows form one 128-byte core matrix, so
+// SBO = 128; LBO = N*16 for the weights and 128*16 + 64 for the activations
+// (see kALbo and ptx.cuh make_smem_desc).
 #pragma once
 #include "../../include/graphcast_b200.h"
 #include "ptx.cuh"
@@ -33,7 +38,13 @@ namespace gcb {
 constexpr int kTileM = 128;
 constexpr int kKStep = 16;
 constexpr int kThreads = 512;
-constexpr int kAPartBytes = kTileM * kKStep * 2;  // 4096: one of {hi, lo}
+// A operand: the two 8-element K chunks of a K-step are 2048 + 64 bytes apart.  The
+// 64-byte skew puts chunk 1 on the other 16 banks so that the producers' 8-byte
+// stores (rows 0-3 of both chunks per half-warp) are conflict-free.
+constexpr int kALbo = kTileM * 16 + 64;           // 2112
+constexpr int kAPartBytes = 2 * kALbo;            // 4224: one of {hi, lo}
+constexpr int kEpiRowFloats = 36;                 // 32 + 4 pad: conflict-free 16 B accesses
+constexpr int kEpiStageBytes = 4 * 32 * kEpiRowFloats * 4;   // per-warp 32x32 transpose tiles
 constexpr int kMaxN = 512;
 constexpr int kMaxKSteps = 128;                   // K <= 2048
 constexpr int kTmemCols = 512;
@@ -45,7 +56,7 @@ struct TcConfig {
   static constexpr int kBStageBytes = kSplit ? kMaxN * kKStep * 4 : kMaxN * kKStep * 2;
   static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
   static constexpr int kParamBytes = 3 * kMaxN * 4;  // bias, ln scale, ln offset
-  static constexpr int kSmemBytes = kStages * kStageBytes + kParamBytes + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kParamBytes + kEpiStageBytes + 512;
 };
 
 __device__ __forceinline__ float swish_f(float x) {
@@ -67,7 +78,8 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
   float* s_bias = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
   float* s_scale = s_bias + kMaxN;
   float* s_offset = s_scale + kMaxN;
-  uint8_t* tail = reinterpret_cast<uint8_t*>(s_offset + kMaxN);
+  float* s_epi = s_offset + kMaxN;                                  // [4][32][36]
+  uint8_t* tail = reinterpret_cast<uint8_t*>(s_epi + 4 * 32 * kEpiRowFloats);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);          // [kStages]
   uint64_t* empty_bar = full_bar + Cfg::kStages;                   // [kStages]
   uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;              // [1]
@@ -82,6 +94,13 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
   int ksteps = 0;
   for (int s = 0; s < d.nseg; ++s) ksteps += d.seg[s].k / kKStep;
   const bool has_ln = d.ln_scale != nullptr;
+  // Cluster schedule: the CTAs of a cluster walk the K-steps of `csize` consecutive
+  // tiles in lockstep and share every weight tile through TMA multicast.
+  const uint32_t crank = ptx::cluster_ctarank();
+  const uint32_t csize = ptx::cluster_nctarank();
+  const uint32_t tile_first = ptx::cluster_id_x() * csize;
+  const uint32_t tile_stride = ptx::num_clusters_x() * csize;
+  const uint16_t cmask = static_cast<uint16_t>((1u << csize) - 1u);
 
   // ---- one-time setup ---------------------------------------------------------
   for (int i = threadIdx.x; i < n; i += kThreads) {
@@ -99,7 +118,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
       }
     for (int s = 0; s < Cfg::kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 5);   // 1 weight producer + 4 activation warps
-      ptx::mbar_init(&empty_bar[s], 1);  // tcgen05.commit
+      ptx::mbar_init(&empty_bar[s], csize);  // tcgen05.commit of every CTA in the cluster
     }
     ptx::mbar_init(tmem_full_bar, 1);
     ptx::mbar_init(tmem_empty_bar, 4);   // 4 epilogue warps
@@ -111,6 +130,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
+  ptx::cluster_sync_all();          // barrier inits visible cluster-wide before remote arrives
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_base_slot;
 
@@ -121,15 +141,23 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
       const uint32_t b_bytes = static_cast<uint32_t>(n) * kKStep * (kSplit ? 4 : 2);
       const size_t b_stride = static_cast<size_t>(n) * kKStep * 4;  // image always holds hi|lo
       const uint8_t* wimg = static_cast<const uint8_t*>(d.w_packed);
+      const uint32_t slice = b_bytes / csize;
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles); base += tile_stride) {
         for (int ks = 0; ks < ksteps; ++ks, ++it) {
           const uint32_t stage = it % Cfg::kStages;
           const uint32_t phase = (it / Cfg::kStages) & 1;
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);     // free in every CTA of the cluster
           ptx::mbar_arrive_expect_tx(&full_bar[stage], b_bytes);
-          ptx::bulk_g2s(stage_base + stage * Cfg::kStageBytes + Cfg::kAStageBytes,
-                        wimg + ks * b_stride, b_bytes, &full_bar[stage]);
+          uint8_t* dst = stage_base + stage * Cfg::kStageBytes + Cfg::kAStageBytes;
+          const uint8_t* src = wimg + ks * b_stride;
+          if (csize == 1) {
+            ptx::bulk_g2s(dst, src, b_bytes, &full_bar[stage]);
+          } else {
+            // Each CTA fetches 1/csize of the tile and multicasts it to all of them.
+            ptx::bulk_g2s_multicast(dst + crank * slice, src + crank * slice, slice,
+                                    &full_bar[stage], cmask);
+          }
         }
       }
     }
@@ -141,7 +169,8 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
       const uint32_t b_lbo = static_cast<uint32_t>(n) * 16;
       const uint32_t b_part = static_cast<uint32_t>(n) * kKStep * 2;
       uint32_t it = 0, tile_iter = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
+      for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles);
+           base += tile_stride, ++tile_iter) {
         ptx::mbar_wait(tmem_empty_bar, (tile_iter & 1) ^ 1);
         ptx::tc_fence_after_sync();
         for (int ks = 0; ks < ksteps; ++ks, ++it) {
@@ -151,8 +180,8 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
           ptx::tc_fence_after_sync();
           const uint32_t sa = ptx::smem_addr(stage_base + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kAStageBytes;
-          const uint64_t a_hi = ptx::make_smem_desc(sa, kTileM * 16, 128);
-          const uint64_t a_lo = ptx::make_smem_desc(sa + kAPartBytes, kTileM * 16, 128);
+          const uint64_t a_hi = ptx::make_smem_desc(sa, kALbo, 128);
+          const uint64_t a_lo = ptx::make_smem_desc(sa + kAPartBytes, kALbo, 128);
           for (uint32_t h = 0; h < n_halves; ++h) {
             const uint32_t boff = h * 256 * 16;
             const uint64_t b_hi = ptx::make_smem_desc(sb + boff, b_lbo, 128);
@@ -164,22 +193,32 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
               ptx::mma_bf16_ss(dcol, a_lo, b_hi, idesc, 1u);
             }
           }
-          ptx::mma_commit(&empty_bar[stage]);   // stage reusable once these MMAs retire
+          // stage reusable (cluster-wide) once these MMAs retire
+          if (csize == 1) ptx::mma_commit(&empty_bar[stage]);
+          else ptx::mma_commit_multicast(&empty_bar[stage], cmask);
         }
         ptx::mma_commit(tmem_full_bar);          // accumulator complete
       }
     }
   } else if (warp >= 4 && warp < 8) {
     // ===== epilogue =====
+    // tcgen05.ld hands each thread one accumulator ROW (32 consecutive columns per
+    // load).  Writing rows straight to global memory from that layout costs 32 cache
+    // lines per warp store, so every 32x32 block is transposed through a padded
+    // per-warp shared-memory tile: 8 lanes then cover one 128-byte row segment and a
+    // warp store writes four complete lines.
     const int ew = warp - 4;                     // == warp % 4: TMEM lane quarter
     const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
     const int n_valid = d.n_valid;
+    float* my_epi = s_epi + ew * 32 * kEpiRowFloats;
+    const int cg = lane & 7;                     // 16-byte column group inside the 32-col block
+    const int rsub = lane >> 3;                  // row within a group of 4
     uint32_t tile_iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
+    for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles);
+         base += tile_stride, ++tile_iter) {
+      const long long row0 = static_cast<long long>(base + crank) * kTileM + ew * 32;
       ptx::mbar_wait(tmem_full_bar, tile_iter & 1);
       ptx::tc_fence_after_sync();
-      const long long grow = static_cast<long long>(tile) * kTileM + ew * 32 + lane;
-      const bool valid = grow < d.rows;
       const uint32_t taddr = tmem_base + lane_base;
       float mean = 0.f, rstd = 1.f;
       if (has_ln) {
@@ -204,7 +243,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
         const float var = fmaxf(s2 * inv_n - m1 * m1, 0.f);
         rstd = rsqrtf(var + 1e-5f);
       }
-      // Pass 2 (or the only pass): finish and store.
+      // Pass 2 (or the only pass): finish, transpose, store.
       for (int c0 = 0; c0 < n_valid; c0 += 32) {
         float v[32];
         ptx::tmem_ld32(taddr + c0, v);
@@ -215,36 +254,42 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
           if (has_ln) x = (x - mean) * rstd * s_scale[c0 + j] + s_offset[c0 + j];
           v[j] = x;
         }
-        if (valid) {
-          const bool full_chunk = (c0 + 32 <= n_valid);
-          if (d.out_y != nullptr) {
-            float* p = d.out_y + grow * d.ld_out_y + c0;
-            if (full_chunk) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(p + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-              for (int j = 0; j < 32 && c0 + j < n_valid; ++j) p[j] = v[j];
-            }
-          }
-          if (d.out != nullptr) {
-            float* p = d.out + grow * d.ld_out + c0;
-            const float* rp = d.residual ? d.residual + grow * d.ld_res + c0 : nullptr;
-            if (full_chunk) {
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(my_epi + lane * kEpiRowFloats + q * 4) =
+              make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        __syncwarp();
+        const int col = c0 + cg * 4;
+        const bool full4 = (col + 4 <= n_valid);
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                if (rp) {
-                  const float4 r = *reinterpret_cast<const float4*>(rp + j);
-                  o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        for (int i = 0; i < 8; ++i) {
+          const int r = rsub + 4 * i;
+          const long long grow = row0 + r;
+          if (grow < d.rows && col < n_valid) {
+            const float4 y = *reinterpret_cast<const float4*>(my_epi + r * kEpiRowFloats + cg * 4);
+            if (full4) {
+              if (d.out_y != nullptr)
+                *reinterpret_cast<float4*>(d.out_y + grow * d.ld_out_y + col) = y;
+              if (d.out != nullptr) {
+                float4 o = y;
+                if (d.residual != nullptr) {
+                  const float4 rr = *reinterpret_cast<const float4*>(d.residual + grow * d.ld_res + col);
+                  o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
                 }
-                *reinterpret_cast<float4*>(p + j) = o;
+                *reinterpret_cast<float4*>(d.out + grow * d.ld_out + col) = o;
               }
             } else {
-              for (int j = 0; j < 32 && c0 + j < n_valid; ++j) p[j] = v[j] + (rp ? rp[j] : 0.f);
+              const float ys[4] = {y.x, y.y, y.z, y.w};
+              for (int e = 0; e < 4 && col + e < n_valid; ++e) {
+                if (d.out_y != nullptr) d.out_y[grow * d.ld_out_y + col + e] = ys[e];
+                if (d.out != nullptr)
+                  d.out[grow * d.ld_out + col + e] =
+                      ys[e] + (d.residual ? d.residual[grow * d.ld_res + col + e] : 0.f);
+              }
             }
           }
         }
+        __syncwarp();
       }
       ptx::tc_fence_before_sync();
       __syncwarp();
@@ -256,9 +301,10 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
     const int tid_g = threadIdx.x - 256 - group * 128;
     const int sub = tid_g & 3;                    // which float4 of the 16-wide K-step
     const int rg = tid_g >> 2;                    // 0..31; rows rg + 32*i
-    const uint32_t sts_off = (sub >> 1) * (kTileM * 16) + (sub & 1) * 8;
+    const uint32_t sts_off = (sub >> 1) * kALbo + (sub & 1) * 8;
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles); base += tile_stride) {
+      const uint32_t tile = base + crank;          // may be past the end: all-zero dummy tile
       // Source row of each of my 4 tile rows, per segment (-1 = out of range).
       long long src[3][4];
 #pragma unroll
@@ -332,8 +378,11 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
   }
 
   // ---- teardown ---------------------------------------------------------------
+  // No CTA may exit while a peer can still multicast into its shared memory or arrive
+  // on its barriers.
   ptx::tc_fence_before_sync();
   __syncthreads();
+  ptx::cluster_sync_all();
   if (warp == 2) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, kTmemCols);

@@ -78,6 +78,46 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
       : "memory");
 }
 
+// Same, multicast to every CTA of the cluster selected by cta_mask: the bytes land at
+// the same CTA-relative offset in each destination CTA and complete_tx is signalled on
+// the mbarrier at the same CTA-relative offset there.
+__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gmem_src,
+                                                   uint32_t bytes, uint64_t* bar,
+                                                   uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_addr(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar)), "h"(cta_mask)
+      : "memory");
+}
+
+// ---- thread-block cluster -----------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t num_clusters_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---- TMEM ---------------------------------------------------------------------
 // Whole-warp, .sync.aligned.  Writes the allocated base address to smem.
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
@@ -160,6 +200,15 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::
                    "r"(smem_addr(bar))
                : "memory");
+}
+
+// Same, arriving on the barrier at the same CTA-relative offset in every CTA of cta_mask.
+__device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(smem_addr(bar)),
+      "h"(cta_mask)
+      : "memory");
 }
 
 // ---- misc ---------------------------------------------------------------------

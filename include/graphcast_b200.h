@@ -106,6 +106,11 @@ int64_t gcb_packed_weight_bytes(int32_t k, int32_t n);
 int gcb_pack_weight_host(const float* w, int32_t k_rows, int32_t n_cols, int32_t k, int32_t n,
                          void* dst);
 
+/* CTAs per thread-block cluster of the tensor-core layer kernel (1, 2 or 4; default
+ * 2).  The CTAs of a cluster process consecutive row tiles in lockstep and receive
+ * each weight tile once from L2 through TMA multicast.  Process-wide tuning knob. */
+int gcb_set_cluster_size(int32_t ctas);
+
 /* Launch one fused layer. */
 int gcb_layer_forward(const gcb_layer_desc* d, void* stream);
 

@@ -1,0 +1,68 @@
+"""Segment sum and channel pack/unpack kernels against PyTorch references."""
+import numpy as np
+import pytest
+import torch
+
+from graphcast_b200 import _native
+
+pytestmark = pytest.mark.gpu
+
+
+def test_segment_sum_skewed_degrees_and_empty_rows():
+  lib = _native.lib()
+  dev = torch.device("cuda:0")
+  rng = np.random.default_rng(0)
+  deg = rng.integers(0, 12, 3000)
+  deg[5] = 0; deg[17] = 3753; deg[2999] = 1             # empty, pole-like, last
+  row_ptr = np.zeros(3001, np.int32); np.cumsum(deg, out=row_ptr[1:])
+  e = int(row_ptr[-1])
+  msg = torch.randn(e, 512, device=dev)
+  out = torch.full((3000, 512), float("nan"), device=dev)
+  rp = torch.as_tensor(row_ptr).to(dev)
+  _native.check(lib.gcb_segment_sum(msg.data_ptr(), 512, rp.data_ptr(), 3000, out.data_ptr(), 512,
+                                    512, torch.cuda.current_stream().cuda_stream), "segsum")
+  ids = torch.repeat_interleave(torch.arange(3000, device=dev), torch.as_tensor(deg, device=dev))
+  want = torch.zeros(3000, 512, device=dev, dtype=torch.float64).index_add_(0, ids, msg.double())
+  torch.testing.assert_close(out.double(), want, rtol=0, atol=2e-4)
+  assert (out[5] == 0).all()
+  # deterministic: bit-identical on a second run
+  out2 = torch.empty_like(out)
+  lib.gcb_segment_sum(msg.data_ptr(), 512, rp.data_ptr(), 3000, out2.data_ptr(), 512, 512,
+                      torch.cuda.current_stream().cuda_stream)
+  assert torch.equal(out, out2)
+
+
+def test_pack_and_unpack_are_exact_transposes_with_affine():
+  lib = _native.lib()
+  dev = torch.device("cuda:0")
+  n_ch, n_nodes, ld, n_out = 37, 1000 + 13, 48, 23
+  planes = torch.randn(n_ch, n_nodes, device=dev)
+  static = torch.randn(n_nodes, 3, device=dev)
+  mean, scale = torch.randn(n_ch, device=dev), torch.rand(n_ch, device=dev) + 0.5
+  feats = torch.full((n_nodes, ld), float("nan"), device=dev)
+  st = torch.cuda.current_stream().cuda_stream
+  _native.check(lib.gcb_pack_grid_features(planes.data_ptr(), n_ch, n_nodes, mean.data_ptr(),
+                                           scale.data_ptr(), static.data_ptr(), 3,
+                                           feats.data_ptr(), ld, st), "pack")
+  want = torch.zeros(n_nodes, ld, device=dev)
+  want[:, :n_ch] = ((planes - mean[:, None]) / scale[:, None]).t()
+  want[:, n_ch:n_ch + 3] = static
+  torch.testing.assert_close(feats, want, rtol=1e-6, atol=1e-6)
+  _native.check(lib.gcb_pack_grid_features(planes.data_ptr(), n_ch, n_nodes, None, None,
+                                           static.data_ptr(), 3, feats.data_ptr(), ld, st), "pack")
+  assert torch.equal(feats[:, :n_ch], planes.t())
+
+  y = torch.randn(n_nodes, 256, device=dev)
+  oscale, ooff = torch.rand(n_out, device=dev) + 0.5, torch.randn(n_out, device=dev)
+  add_idx = torch.arange(n_out, dtype=torch.int32, device=dev) + 3
+  add_idx[4] = -1
+  out = torch.full((n_out, n_nodes), float("nan"), device=dev)
+  _native.check(lib.gcb_unpack_grid_outputs(y.data_ptr(), 256, n_out, n_nodes, oscale.data_ptr(),
+                                            ooff.data_ptr(), planes.data_ptr(), add_idx.data_ptr(),
+                                            out.data_ptr(), st), "unpack")
+  want = y[:, :n_out].t() * oscale[:, None] + ooff[:, None]
+  add = planes[(add_idx.clamp(min=0)).long()] * (add_idx >= 0)[:, None]
+  torch.testing.assert_close(out, want + add, rtol=1e-6, atol=1e-6)
+  _native.check(lib.gcb_unpack_grid_outputs(y.data_ptr(), 256, n_out, n_nodes, None, None, None,
+                                            None, out.data_ptr(), st), "unpack")
+  assert torch.equal(out, y[:, :n_out].t().contiguous())

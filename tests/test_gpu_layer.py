@@ -1,0 +1,153 @@
+"""Parity of the fused layer kernel (through the C ABI) against a plain PyTorch
+fp32/fp64 reference of the same op: gathers, fan-in sums, zero padding, bias,
+swish, LayerNorm, residual, both outputs, ragged row counts, both output widths."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from graphcast_b200 import _native
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"bf16x3": 3e-5, "bf16": 2e-2, "fp32_simt": 2e-6}
+
+
+def _pack(lib, w, k_pad, n_pad, dev):
+  img = np.empty(lib.gcb_packed_weight_bytes(k_pad, n_pad), np.uint8)
+  wp = np.zeros((k_pad, n_pad), np.float32)
+  wp[:w.shape[0], :w.shape[1]] = w
+  assert lib.gcb_pack_weight_host(wp.ctypes.data, k_pad, n_pad, k_pad, n_pad, img.ctypes.data) == 0
+  return torch.as_tensor(img).to(dev), torch.as_tensor(wp).to(dev)
+
+
+def _run_case(prec, rows, segs, n, n_valid, act, ln, residual, out_y, seed=0):
+  """segs: list of (table_rows, k_valid, k_pad, use_idx, fan)."""
+  lib = _native.lib()
+  dev = torch.device("cuda:0")
+  g = torch.Generator().manual_seed(seed)
+  d = _native.LayerDesc()
+  d.rows, d.n, d.n_valid, d.nseg = rows, n, n_valid, len(segs)
+  keep, cols, w_rows = [], [], []
+  for i, (trows, kv, kp, use_idx, fan) in enumerate(segs):
+    ld = kv + 4                                   # row stride wider than the data
+    table = torch.randn(trows * fan, ld, generator=g)
+    idx = torch.randint(0, trows, (rows,), generator=g, dtype=torch.int32) if use_idx else None
+    tdev = table.to(dev); keep.append(tdev)
+    d.seg[i].table, d.seg[i].ld, d.seg[i].k, d.seg[i].k_valid, d.seg[i].fan = tdev.data_ptr(), ld, kp, kv, fan
+    if idx is not None:
+      idev = idx.to(dev); keep.append(idev); d.seg[i].idx = idev.data_ptr()
+    src = idx.long() if idx is not None else torch.arange(rows)
+    assert trows >= rows or use_idx
+    gathered = table.view(trows, fan, ld)[src][:, :, :kv].double().sum(1)
+    cols.append(gathered)
+    w_rows.append((kv, kp))
+  k_real = sum(kv for kv, _ in w_rows)
+  w = torch.randn(k_real, n_valid, generator=g) / np.sqrt(k_real)
+  # lay weight rows out with per-segment padding
+  k_pad = sum(kp for _, kp in w_rows)
+  wp = np.zeros((k_pad, n_valid), np.float32)
+  s = dst = 0
+  for kv, kp in w_rows:
+    wp[dst:dst + kv] = w[s:s + kv].numpy(); s += kv; dst += kp
+  img, wf = _pack(lib, wp, k_pad, n, dev)
+  bias = torch.randn(n, generator=g) * 0.1
+  scale = 1 + 0.1 * torch.randn(n, generator=g)
+  offset = 0.1 * torch.randn(n, generator=g)
+  bdev, sdev, odev = bias.to(dev), scale.to(dev), offset.to(dev)
+  d.w_packed, d.w_f32, d.bias = img.data_ptr(), wf.data_ptr(), bdev.data_ptr()
+  if ln:
+    d.ln_scale, d.ln_offset = sdev.data_ptr(), odev.data_ptr()
+  d.act = 1 if act else 0
+  ld_out = n_valid + (4 - n_valid % 4) % 4 + 4
+  res = torch.randn(rows, ld_out, generator=g)
+  rdev = res.to(dev)
+  out = torch.full((rows, ld_out), float("nan"), device=dev)
+  outy = torch.full((rows, 512), float("nan"), device=dev)
+  if residual:
+    d.residual, d.ld_res = rdev.data_ptr(), ld_out
+  d.out, d.ld_out = out.data_ptr(), ld_out
+  if out_y:
+    d.out_y, d.ld_out_y = outy.data_ptr(), 512
+  d.precision = _native.PRECISIONS[prec]
+  _native.check(lib.gcb_layer_forward(C.byref(d), torch.cuda.current_stream().cuda_stream), "layer")
+  torch.cuda.synchronize()
+  # reference in float64
+  z = torch.cat(cols, 1)
+  y = z @ w.double() + bias[:n_valid].double()
+  if act:
+    y = y * torch.sigmoid(y)
+  if ln:
+    y = torch.nn.functional.layer_norm(y, (n_valid,), scale[:n_valid].double(), offset[:n_valid].double(), 1e-5)
+  want = y + (res[:, :n_valid].double() if residual else 0)
+  got = out[:, :n_valid].cpu().double()
+  denom = want.abs().max()
+  err = float((got - want).abs().max() / denom)
+  assert torch.isnan(out[:, n_valid:]).all(), "kernel wrote beyond n_valid"
+  if out_y:
+    erry = float((outy[:, :n_valid].cpu().double() - y).abs().max() / y.abs().max())
+    err = max(err, erry)
+  return err
+
+
+@pytest.mark.parametrize("prec", ["fp32_simt", "bf16x3", "bf16"])
+def test_edge_block_three_gathered_segments(prec):
+  err = _run_case(prec, rows=1000, segs=[(1000, 512, 512, False, 1), (300, 512, 512, True, 1),
+                                         (77, 512, 512, True, 1)],
+                  n=512, n_valid=512, act=True, ln=False, residual=False, out_y=False)
+  assert err < TOL[prec], err
+
+
+@pytest.mark.parametrize("prec", ["fp32_simt", "bf16x3", "bf16"])
+def test_layernorm_residual_and_message_output(prec):
+  err = _run_case(prec, rows=333, segs=[(333, 512, 512, False, 1)], n=512, n_valid=512,
+                  act=False, ln=True, residual=True, out_y=True)
+  assert err < TOL[prec], err
+
+
+@pytest.mark.parametrize("prec", ["fp32_simt", "bf16x3"])
+def test_padded_inputs_and_narrow_output(prec):
+  # K=474 real columns padded to 480 (first encoder layer), K=4 padded to 16 (edge embed)
+  err = _run_case(prec, rows=257, segs=[(257, 476, 480, False, 1)], n=512, n_valid=512,
+                  act=True, ln=False, residual=False, out_y=False)
+  assert err < TOL[prec], err
+  err = _run_case(prec, rows=129, segs=[(129, 4, 16, False, 1)], n=512, n_valid=512,
+                  act=True, ln=False, residual=False, out_y=False)
+  assert err < TOL[prec], err
+  # decoder output layer: 227 of 256 columns, no LayerNorm
+  err = _run_case(prec, rows=500, segs=[(500, 512, 512, False, 1)], n=256, n_valid=227,
+                  act=False, ln=False, residual=False, out_y=False)
+  assert err < TOL[prec], err
+
+
+@pytest.mark.parametrize("prec", ["fp32_simt", "bf16x3"])
+def test_fan_in_three_segment(prec):
+  err = _run_case(prec, rows=700, segs=[(700, 512, 512, False, 1), (700, 512, 512, False, 3)],
+                  n=512, n_valid=512, act=True, ln=False, residual=False, out_y=False)
+  assert err < TOL[prec], err
+
+
+@pytest.mark.parametrize("rows", [1, 127, 128, 129, 148 * 128 + 5])
+def test_ragged_row_counts(rows):
+  err = _run_case("bf16x3", rows=rows, segs=[(max(rows, 1), 512, 512, False, 1)], n=512,
+                  n_valid=512, act=False, ln=True, residual=True, out_y=False)
+  assert err < TOL["bf16x3"], err
+
+
+def test_zero_rows_is_a_noop():
+  lib = _native.lib()
+  d = _native.LayerDesc()
+  t = torch.zeros(16, 16, device="cuda:0")
+  d.rows, d.n, d.n_valid, d.nseg = 0, 512, 512, 1
+  d.seg[0].table, d.seg[0].ld, d.seg[0].k, d.seg[0].k_valid, d.seg[0].fan = t.data_ptr(), 16, 16, 16, 1
+  d.w_packed, d.bias, d.out, d.ld_out = t.data_ptr(), t.data_ptr(), t.data_ptr(), 512
+  assert lib.gcb_layer_forward(C.byref(d), None) == 0
+
+
+def test_tensor_path_matches_simt_arm_selftest():
+  lib = _native.lib()
+  for prec, tol in (("bf16x3", 3e-5), ("bf16", 2e-2)):
+    err = C.c_float(-1)
+    assert lib.gcb_selftest_layer(3000, 1024, 512, _native.PRECISIONS[prec], C.byref(err)) == 0
+    assert 0 <= err.value < tol
