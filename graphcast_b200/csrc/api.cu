@@ -441,6 +441,12 @@ int gcb_set_cluster_size(int32_t ctas) {
   return GCB_OK;
 }
 
+int gcb_debug_trace(long long* device_buffer) {
+  // device_buffer: [kTraceTiles * kTraceEvents] int64 on the device, or NULL to disable.
+  GCB_CUDA(cudaMemcpyToSymbol(gcb::g_trace, &device_buffer, sizeof(device_buffer)));
+  return GCB_OK;
+}
+
 int gcb_profile_begin(void) {
   for (auto& r : g_prof) { g_event_pool.push_back(r.beg); g_event_pool.push_back(r.end); }
   g_prof.clear();

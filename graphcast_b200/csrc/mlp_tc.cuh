@@ -64,6 +64,17 @@ __device__ __forceinline__ float swish_f(float x) {
   return x * __frcp_rn(1.0f + __expf(-x));
 }
 
+// Optional timeline trace (debug): when non-null, CTA 0 records clock64() at a few
+// points of each of its first kTraceTiles tiles; see gcb_debug_trace in api.cu.
+constexpr int kTraceTiles = 64;
+constexpr int kTraceEvents = 8;
+__device__ long long* g_trace = nullptr;
+
+__device__ __forceinline__ void trace(uint32_t tile_iter, int ev) {
+  if (g_trace != nullptr && blockIdx.x == 0 && tile_iter < kTraceTiles)
+    g_trace[tile_iter * kTraceEvents + ev] = clock64();
+}
+
 struct KStepInfo {
   uint8_t seg;
   uint16_t koff;  // element offset of this K-step inside its segment
@@ -173,11 +184,13 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
            base += tile_stride, ++tile_iter) {
         ptx::mbar_wait(tmem_empty_bar, (tile_iter & 1) ^ 1);
         ptx::tc_fence_after_sync();
+        trace(tile_iter, 0);
         for (int ks = 0; ks < ksteps; ++ks, ++it) {
           const uint32_t stage = it % Cfg::kStages;
           const uint32_t phase = (it / Cfg::kStages) & 1;
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after_sync();
+          if (ks == 0) trace(tile_iter, 1);
           const uint32_t sa = ptx::smem_addr(stage_base + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kAStageBytes;
           const uint64_t a_hi = ptx::make_smem_desc(sa, kALbo, 128);
@@ -198,6 +211,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
           else ptx::mma_commit_multicast(&empty_bar[stage], cmask);
         }
         ptx::mma_commit(tmem_full_bar);          // accumulator complete
+        trace(tile_iter, 2);
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -219,6 +233,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
       const long long row0 = static_cast<long long>(base + crank) * kTileM + ew * 32;
       ptx::mbar_wait(tmem_full_bar, tile_iter & 1);
       ptx::tc_fence_after_sync();
+      if (ew == 0 && lane == 0) trace(tile_iter, 3);
       const uint32_t taddr = tmem_base + lane_base;
       float mean = 0.f, rstd = 1.f;
       if (has_ln) {
@@ -243,6 +258,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
         const float var = fmaxf(s2 * inv_n - m1 * m1, 0.f);
         rstd = rsqrtf(var + 1e-5f);
       }
+      if (ew == 0 && lane == 0) trace(tile_iter, 4);
       // Pass 2 (or the only pass): finish, transpose, store.
       for (int c0 = 0; c0 < n_valid; c0 += 32) {
         float v[32];
@@ -291,6 +307,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
         }
         __syncwarp();
       }
+      if (ew == 0 && lane == 0) trace(tile_iter, 5);
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tmem_empty_bar);

@@ -222,6 +222,13 @@ int gcb_profile_begin(void);
 int gcb_profile_end(int32_t capacity, int32_t* kinds, float* ms, double* flops, double* bytes,
                     int32_t* count);
 
+/* Debug: timeline trace of CTA 0 of the tensor-core layer kernel.  `device_buffer`
+ * (64 tiles x 8 events of int64 clock64 values; NULL disables) receives, per tile:
+ * [0] MMA: accumulator free  [1] MMA: first operands landed  [2] MMA: last commit issued
+ * [3] epilogue: accumulator ready  [4] epilogue: LayerNorm statistics done
+ * [5] epilogue: tile stored. */
+int gcb_debug_trace(long long* device_buffer);
+
 /* Device self-test of the tensor-core layer against the FP32_SIMT arm on random
  * data (used by tests and __graft_entry__.smoke); returns max |diff| / max |ref|
  * through *rel_err.  Allocates its own scratch. */

@@ -1,0 +1,54 @@
+"""Timeline of CTA 0 for one fused-layer launch (debug aid)."""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from graphcast_b200 import _native
+lib = _native.lib()
+dev = torch.device("cuda:0")
+
+def run(rows, k, n, ln, act, csize, out_y=False, residual=False, idx=False):
+  lib.gcb_set_cluster_size(csize)
+  a = torch.randn(rows, k, device=dev)
+  w = (torch.randn(k, n) / np.sqrt(k)).numpy().astype(np.float32)
+  img = np.empty(lib.gcb_packed_weight_bytes(k, n), np.uint8)
+  lib.gcb_pack_weight_host(w.ctypes.data, k, n, k, n, img.ctypes.data)
+  img_d = torch.as_tensor(img).to(dev)
+  bias = torch.zeros(n, device=dev); sc = torch.ones(n, device=dev); of = torch.zeros(n, device=dev)
+  out = torch.empty(rows, n, device=dev); oy = torch.empty(rows, 512, device=dev); res = torch.randn(rows, n, device=dev)
+  d = _native.LayerDesc()
+  d.rows, d.n, d.n_valid, d.nseg = rows, n, n, 1
+  d.seg[0].table, d.seg[0].ld, d.seg[0].k, d.seg[0].k_valid, d.seg[0].fan = a.data_ptr(), k, k, k, 1
+  if idx:
+    ix = torch.randint(0, rows, (rows,), dtype=torch.int32, device=dev); d.seg[0].idx = ix.data_ptr()
+  d.w_packed, d.bias = img_d.data_ptr(), bias.data_ptr()
+  if ln: d.ln_scale, d.ln_offset = sc.data_ptr(), of.data_ptr()
+  d.act = 1 if act else 0
+  d.out, d.ld_out = out.data_ptr(), n
+  if out_y: d.out_y, d.ld_out_y = oy.data_ptr(), 512
+  if residual: d.residual, d.ld_res = res.data_ptr(), n
+  d.precision = 0
+  tr = torch.zeros(64 * 8, dtype=torch.int64, device=dev)
+  for _ in range(2):
+    lib.gcb_layer_forward(C.byref(d), None)
+  torch.cuda.synchronize()
+  lib.gcb_debug_trace(tr.data_ptr())
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record(); lib.gcb_layer_forward(C.byref(d), None); e1.record()
+  torch.cuda.synchronize()
+  lib.gcb_debug_trace(None)
+  t = tr.cpu().numpy().reshape(64, 8)
+  ntile = min(64, (rows + 127) // 128 // 148)
+  print(f"rows={rows} k={k} n={n} ln={ln} act={act} cluster={csize} out_y={out_y} res={residual} idx={idx}: {e0.elapsed_time(e1):.3f} ms; tiles/CTA~{ntile}")
+  base = t[1, 0]
+  for i in range(1, min(ntile, 6)):
+    r = t[i]
+    print(f"  tile {i}: acc_free@{r[0]-base:7d} ops_ready+{r[1]-r[0]:6d} mma_issue+{r[2]-r[1]:6d} | "
+          f"epi_start(after commit)+{r[3]-r[2]:6d} ln_stats+{r[4]-r[3]:6d} store+{r[5]-r[4]:6d} | "
+          f"next_acc_free+{t[i+1,0]-r[5]:6d}  tile_total={t[i+1,0]-r[0]}")
+
+rows = 148 * 128 * 8
+for cs in (1, 2):
+  run(rows, 16, 512, False, True, cs)
+  run(rows, 512, 512, True, False, cs)
+  run(rows, 512, 512, True, False, cs, out_y=True, residual=True)
+  run(rows, 1536, 512, False, True, cs, idx=True)
