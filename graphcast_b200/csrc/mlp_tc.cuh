@@ -80,6 +80,14 @@ struct KStepInfo {
   uint16_t koff;  // element offset of this K-step inside its segment
 };
 
+// Per-segment fields copied to shared memory once: reading them from the kernel
+// parameter (constant bank) inside the hot loops costs an exposed ~100-cycle LDC each.
+struct SegInfo {
+  const float* table;
+  const int32_t* idx;
+  int ld, k_valid, fan, pad;
+};
+
 template <bool kSplit>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
@@ -96,7 +104,8 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
   uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;              // [1]
   uint64_t* tmem_empty_bar = tmem_full_bar + 1;                    // [1]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
-  KStepInfo* ks_info = reinterpret_cast<KStepInfo*>(tmem_base_slot + 2);  // [kMaxKSteps]
+  SegInfo* s_seg = reinterpret_cast<SegInfo*>(tmem_base_slot + 2);        // [3]
+  KStepInfo* ks_info = reinterpret_cast<KStepInfo*>(s_seg + 3);           // [kMaxKSteps]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -105,6 +114,14 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
   int ksteps = 0;
   for (int s = 0; s < d.nseg; ++s) ksteps += d.seg[s].k / kKStep;
   const bool has_ln = d.ln_scale != nullptr;
+  // Descriptor fields used inside hot loops, hoisted into registers once.
+  const long long rows_total = d.rows;
+  const int nseg = d.nseg;
+  const bool do_swish = d.act == GCB_ACT_SWISH;
+  float* const out_ptr = d.out;
+  float* const outy_ptr = d.out_y;
+  const float* const res_ptr = d.residual;
+  const long long ld_out = d.ld_out, ld_outy = d.ld_out_y, ld_res = d.ld_res;
   // Cluster schedule: the CTAs of a cluster walk the K-steps of `csize` consecutive
   // tiles in lockstep and share every weight tile through TMA multicast.
   const uint32_t crank = ptx::cluster_ctarank();
@@ -121,6 +138,13 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
   }
   if (threadIdx.x == 0) {
     int ks = 0;
+    for (int s = 0; s < d.nseg; ++s) {
+      s_seg[s].table = d.seg[s].table;
+      s_seg[s].idx = d.seg[s].idx;
+      s_seg[s].ld = d.seg[s].ld;
+      s_seg[s].k_valid = d.seg[s].k_valid;
+      s_seg[s].fan = d.seg[s].fan;
+    }
     for (int s = 0; s < d.nseg; ++s)
       for (int k = 0; k < d.seg[s].k; k += kKStep) {
         ks_info[ks].seg = static_cast<uint8_t>(s);
@@ -266,7 +290,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float x = v[j] + s_bias[c0 + j];
-          if (d.act == GCB_ACT_SWISH) x = swish_f(x);
+          if (do_swish) x = swish_f(x);
           if (has_ln) x = (x - mean) * rstd * s_scale[c0 + j] + s_offset[c0 + j];
           v[j] = x;
         }
@@ -281,26 +305,26 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
         for (int i = 0; i < 8; ++i) {
           const int r = rsub + 4 * i;
           const long long grow = row0 + r;
-          if (grow < d.rows && col < n_valid) {
+          if (grow < rows_total && col < n_valid) {
             const float4 y = *reinterpret_cast<const float4*>(my_epi + r * kEpiRowFloats + cg * 4);
             if (full4) {
-              if (d.out_y != nullptr)
-                *reinterpret_cast<float4*>(d.out_y + grow * d.ld_out_y + col) = y;
-              if (d.out != nullptr) {
+              if (outy_ptr != nullptr)
+                *reinterpret_cast<float4*>(outy_ptr + grow * ld_outy + col) = y;
+              if (out_ptr != nullptr) {
                 float4 o = y;
-                if (d.residual != nullptr) {
-                  const float4 rr = *reinterpret_cast<const float4*>(d.residual + grow * d.ld_res + col);
+                if (res_ptr != nullptr) {
+                  const float4 rr = *reinterpret_cast<const float4*>(res_ptr + grow * ld_res + col);
                   o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
                 }
-                *reinterpret_cast<float4*>(d.out + grow * d.ld_out + col) = o;
+                *reinterpret_cast<float4*>(out_ptr + grow * ld_out + col) = o;
               }
             } else {
               const float ys[4] = {y.x, y.y, y.z, y.w};
               for (int e = 0; e < 4 && col + e < n_valid; ++e) {
-                if (d.out_y != nullptr) d.out_y[grow * d.ld_out_y + col + e] = ys[e];
-                if (d.out != nullptr)
-                  d.out[grow * d.ld_out + col + e] =
-                      ys[e] + (d.residual ? d.residual[grow * d.ld_res + col + e] : 0.f);
+                if (outy_ptr != nullptr) outy_ptr[grow * ld_outy + col + e] = ys[e];
+                if (out_ptr != nullptr)
+                  out_ptr[grow * ld_out + col + e] =
+                      ys[e] + (res_ptr ? res_ptr[grow * ld_res + col + e] : 0.f);
               }
             }
           }
@@ -329,10 +353,10 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           src[s][i] = -1;
-          if (s < d.nseg) {
+          if (s < nseg) {
             const long long grow = static_cast<long long>(tile) * kTileM + rg + 32 * i;
-            if (grow < d.rows)
-              src[s][i] = d.seg[s].idx ? static_cast<long long>(d.seg[s].idx[grow]) : grow;
+            const int32_t* ip = s_seg[s].idx;
+            if (grow < rows_total) src[s][i] = ip ? static_cast<long long>(__ldg(ip + grow)) : grow;
           }
         }
       }
@@ -348,7 +372,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
         if (mine) {
           const int s = ks_info[ks].seg;
           const int koff = ks_info[ks].koff + sub * 4;
-          const gcb_segment& sg = d.seg[s];
+          const SegInfo sg = s_seg[s];
           const bool kvalid = koff < sg.k_valid;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
