@@ -56,7 +56,7 @@ struct TcConfig {
   static constexpr int kBStageBytes = kSplit ? kMaxN * kKStep * 4 : kMaxN * kKStep * 2;
   static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
   static constexpr int kParamBytes = 3 * kMaxN * 4;  // bias, ln scale, ln offset
-  static constexpr int kSmemBytes = kStages * kStageBytes + kParamBytes + kEpiStageBytes + 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kParamBytes + kEpiStageBytes + 1024;
 };
 
 __device__ __forceinline__ float swish_f(float x) {
@@ -283,8 +283,20 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
         rstd = rsqrtf(var + 1e-5f);
       }
       if (ew == 0 && lane == 0) trace(tile_iter, 4);
-      // Pass 2 (or the only pass): finish, transpose, store.
+      // Pass 2 (or the only pass): finish, transpose, store.  Only one warp per SM
+      // sub-partition runs this, so nothing hides latency for it: the fast path is
+      // branch-free and batches its loads (residual rows are requested before the
+      // TMEM read, the eight shared-memory reads are issued back to back).
+      const bool rows_full = row0 + 32 <= rows_total;
       for (int c0 = 0; c0 < n_valid; c0 += 32) {
+        const int col = c0 + cg * 4;
+        const bool fast = rows_full && (c0 + 32 <= n_valid);
+        float4 rr[8];
+        if (fast && res_ptr != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            rr[i] = *reinterpret_cast<const float4*>(res_ptr + (row0 + rsub + 4 * i) * ld_res + col);
+        }
         float v[32];
         ptx::tmem_ld32(taddr + c0, v);
 #pragma unroll
@@ -299,32 +311,39 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
           *reinterpret_cast<float4*>(my_epi + lane * kEpiRowFloats + q * 4) =
               make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         __syncwarp();
-        const int col = c0 + cg * 4;
-        const bool full4 = (col + 4 <= n_valid);
+        if (fast) {
+          float4 y[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = rsub + 4 * i;
-          const long long grow = row0 + r;
-          if (grow < rows_total && col < n_valid) {
-            const float4 y = *reinterpret_cast<const float4*>(my_epi + r * kEpiRowFloats + cg * 4);
-            if (full4) {
-              if (outy_ptr != nullptr)
-                *reinterpret_cast<float4*>(outy_ptr + grow * ld_outy + col) = y;
-              if (out_ptr != nullptr) {
-                float4 o = y;
-                if (res_ptr != nullptr) {
-                  const float4 rr = *reinterpret_cast<const float4*>(res_ptr + grow * ld_res + col);
-                  o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-                }
-                *reinterpret_cast<float4*>(out_ptr + grow * ld_out + col) = o;
+          for (int i = 0; i < 8; ++i)
+            y[i] = *reinterpret_cast<const float4*>(my_epi + (rsub + 4 * i) * kEpiRowFloats + cg * 4);
+          if (outy_ptr != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<float4*>(outy_ptr + (row0 + rsub + 4 * i) * ld_outy + col) = y[i];
+          }
+          if (out_ptr != nullptr) {
+            if (res_ptr != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                y[i].x += rr[i].x; y[i].y += rr[i].y; y[i].z += rr[i].z; y[i].w += rr[i].w;
               }
-            } else {
-              const float ys[4] = {y.x, y.y, y.z, y.w};
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<float4*>(out_ptr + (row0 + rsub + 4 * i) * ld_out + col) = y[i];
+          }
+        } else {
+          // Ragged edge (last rows of the matrix / last partial column block).
+          for (int i = 0; i < 8; ++i) {
+            const int r = rsub + 4 * i;
+            const long long grow = row0 + r;
+            if (grow < rows_total) {
               for (int e = 0; e < 4 && col + e < n_valid; ++e) {
-                if (outy_ptr != nullptr) outy_ptr[grow * ld_outy + col + e] = ys[e];
+                const float yv = my_epi[r * kEpiRowFloats + cg * 4 + e];
+                if (outy_ptr != nullptr) outy_ptr[grow * ld_outy + col + e] = yv;
                 if (out_ptr != nullptr)
                   out_ptr[grow * ld_out + col + e] =
-                      ys[e] + (res_ptr ? res_ptr[grow * ld_res + col + e] : 0.f);
+                      yv + (res_ptr ? res_ptr[grow * ld_res + col + e] : 0.f);
               }
             }
           }
