@@ -138,17 +138,18 @@ int validate_layer(const gcb_layer_desc* d) {
 
 int g_cluster_size = 2;   // CTAs per cluster sharing the weight stream (1, 2 or 4)
 
-template <bool kSplit>
-int launch_tc(const gcb_layer_desc& d, cudaStream_t stream) {
+template <bool kSplit, bool kSwish, bool kLN>
+int launch_tc_variant(const gcb_layer_desc& d, cudaStream_t stream) {
   using Cfg = gcb::TcConfig<kSplit>;
+  auto kernel = gcb::mlp_layer_tc_kernel<kSplit, kSwish, kLN>;
   static bool attr_set[64] = {false};
   static int max_clusters[64][5] = {{0}};
   int dev = 0;
   GCB_CUDA(cudaGetDevice(&dev));
   GCB_CHECK_ARG(dev >= 0 && dev < 64, "device index out of range");
   if (!attr_set[dev]) {
-    GCB_CUDA(cudaFuncSetAttribute(gcb::mlp_layer_tc_kernel<kSplit>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    GCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::kSmemBytes));
     attr_set[dev] = true;
   }
   const int csize = g_cluster_size;
@@ -167,7 +168,7 @@ int launch_tc(const gcb_layer_desc& d, cudaStream_t stream) {
   if (max_clusters[dev][csize] == 0) {
     cfg.gridDim = dim3(sm_count_cached() / csize * csize);
     int nc = 0;
-    GCB_CUDA(cudaOccupancyMaxActiveClusters(&nc, gcb::mlp_layer_tc_kernel<kSplit>, &cfg));
+    GCB_CUDA(cudaOccupancyMaxActiveClusters(&nc, kernel, &cfg));
     if (nc <= 0) return fail(GCB_ERR_CUDA, "no resident cluster fits on this device");
     max_clusters[dev][csize] = nc;
   }
@@ -175,8 +176,17 @@ int launch_tc(const gcb_layer_desc& d, cudaStream_t stream) {
   int clusters = (tiles + csize - 1) / csize;
   if (clusters > max_clusters[dev][csize]) clusters = max_clusters[dev][csize];
   cfg.gridDim = dim3(clusters * csize);
-  GCB_CUDA(cudaLaunchKernelEx(&cfg, gcb::mlp_layer_tc_kernel<kSplit>, d));
+  GCB_CUDA(cudaLaunchKernelEx(&cfg, kernel, d));
   return GCB_OK;
+}
+
+template <bool kSplit>
+int launch_tc(const gcb_layer_desc& d, cudaStream_t stream) {
+  const bool swish = d.act == GCB_ACT_SWISH, ln = d.ln_scale != nullptr;
+  if (swish && ln) return launch_tc_variant<kSplit, true, true>(d, stream);
+  if (swish) return launch_tc_variant<kSplit, true, false>(d, stream);
+  if (ln) return launch_tc_variant<kSplit, false, true>(d, stream);
+  return launch_tc_variant<kSplit, false, false>(d, stream);
 }
 
 int launch_simt(const gcb_layer_desc& d, cudaStream_t stream) {
