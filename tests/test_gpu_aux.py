@@ -23,7 +23,8 @@ def test_segment_sum_skewed_degrees_and_empty_rows():
                                     512, torch.cuda.current_stream().cuda_stream), "segsum")
   ids = torch.repeat_interleave(torch.arange(3000, device=dev), torch.as_tensor(deg, device=dev))
   want = torch.zeros(3000, 512, device=dev, dtype=torch.float64).index_add_(0, ids, msg.double())
-  torch.testing.assert_close(out.double(), want, rtol=0, atol=2e-4)
+  # fp32 running sums of up to 3753 N(0,1) terms: absolute error grows with the degree
+  torch.testing.assert_close(out.double(), want, rtol=1e-5, atol=2e-3)
   assert (out[5] == 0).all()
   # deterministic: bit-identical on a second run
   out2 = torch.empty_like(out)
