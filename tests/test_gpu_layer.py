@@ -11,7 +11,7 @@ from graphcast_b200 import _native
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"bf16x3": 3e-5, "bf16": 2e-2, "fp32_simt": 2e-6}
+TOL = {"bf16x3": 3e-5, "bf16": 2e-2, "fp32_simt": 5e-6}
 
 
 def _pack(lib, w, k_pad, n_pad, dev):
