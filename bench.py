@@ -236,7 +236,8 @@ def run_b200(args):
   inputs, template, forcings = synthetic.make_example(task, res, batch=1, seed=rank,
                                                       pinned=True)
   params = graphcast.init_params(cfg, task, c_in, seed=1)
-  model = graphcast.GraphCast(cfg, task, params=params, precision=args.precision, device=dev)
+  model = graphcast.GraphCast(cfg, task, params=params, precision=args.precision, device=dev,
+                              pregather=args.pregather)
   # First call builds the static graph, uploads weights, allocates the workspace.
   pred = model(inputs, template, forcings)
   torch.cuda.synchronize()
@@ -363,6 +364,7 @@ def run_b200(args):
         "config": {"workload": args.workload, "resolution_deg": res, "mesh_size": mesh,
                    "levels": len(task.pressure_levels), "latent": 512, "msg_steps": 16,
                    "batch": 1, "precision": args.precision, "cluster": args.cluster or "default(2)",
+                   "pregather": bool(args.pregather),
                    "parallelism": "1 forecast per GPU (ensemble members), no collective",
                    "l2_policy": "working set per step (>20 GB) far exceeds the 126 MB L2; no flush needed",
                    "setup_s": setup_s},
@@ -392,6 +394,8 @@ def main():
   ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=5)
   ap.add_argument("--skip-cpu-baseline", action="store_true")
   ap.add_argument("--cluster", type=int, default=0, help="CTAs per cluster (0 = library default)")
+  ap.add_argument("--no-pregather", dest="pregather", action="store_false",
+                  help="evaluate the first edge-MLP layer over the concatenated K=1536 input")
   args = ap.parse_args()
   if args.impl == "reference":
     run_reference(args)

@@ -27,6 +27,10 @@ class Segment(C.Structure):
               ("k_valid", C.c_int32), ("fan", C.c_int32)]
 
 
+class PreAdd(C.Structure):
+  _fields_ = [("table", _fp), ("idx", _fp), ("ld", C.c_int32), ("pad_", C.c_int32)]
+
+
 class LayerDesc(C.Structure):
   _fields_ = [("rows", C.c_int32), ("n", C.c_int32), ("n_valid", C.c_int32),
               ("nseg", C.c_int32), ("seg", Segment * 3),
@@ -35,7 +39,12 @@ class LayerDesc(C.Structure):
               ("residual", _fp), ("ld_res", C.c_int32),
               ("out", _fp), ("ld_out", C.c_int32),
               ("out_y", _fp), ("ld_out_y", C.c_int32),
-              ("precision", C.c_int32)]
+              ("precision", C.c_int32), ("n_pre_add", C.c_int32), ("pre_add", PreAdd * 2)]
+
+
+class MlpSplit(C.Structure):
+  _fields_ = [("we_packed", _fp), ("we_f32", _fp), ("ws_packed", _fp), ("ws_f32", _fp),
+              ("wr_packed", _fp), ("wr_f32", _fp)]
 
 
 class Mlp(C.Structure):
@@ -50,7 +59,7 @@ class Model(C.Structure):
       ("num_grid", C.c_int32), ("num_mesh", C.c_int32),
       ("e_g2m", C.c_int32), ("e_mesh", C.c_int32), ("e_m2g", C.c_int32),
       ("c_in_pad", C.c_int32), ("c_in_valid", C.c_int32),
-      ("msg_steps", C.c_int32), ("precision", C.c_int32),
+      ("msg_steps", C.c_int32), ("precision", C.c_int32), ("pregather", C.c_int32),
       ("g2m_snd", _fp), ("g2m_rcv", _fp), ("g2m_row_ptr", _fp), ("g2m_feat", _fp),
       ("mesh_snd", _fp), ("mesh_rcv", _fp), ("mesh_row_ptr", _fp), ("mesh_feat", _fp),
       ("m2g_snd", _fp), ("m2g_rcv", _fp), ("m2g_feat", _fp),
@@ -61,6 +70,9 @@ class Model(C.Structure):
       ("proc_e_mesh", Mlp * GCB_MAX_MSG_STEPS),
       ("proc_n_mesh", Mlp * GCB_MAX_MSG_STEPS),
       ("enc_e_m2g", Mlp), ("proc_e_m2g", Mlp), ("proc_n_grid_m2g", Mlp), ("dec_grid", Mlp),
+      ("proc_e_g2m_split", MlpSplit), ("proc_e_m2g_split", MlpSplit),
+      ("proc_e_mesh_split", MlpSplit * GCB_MAX_MSG_STEPS),
+      ("zero_bias", _fp), ("proj_grid", _fp), ("proj_mesh_a", _fp), ("proj_mesh_b", _fp),
       ("hidden", _fp), ("edge_a", _fp), ("edge_b", _fp), ("grid_lat", _fp),
       ("mesh_lat", _fp), ("mesh_agg", _fp), ("mesh_edge", _fp), ("mesh_msg", _fp),
   ]

@@ -127,6 +127,15 @@ int validate_layer(const gcb_layer_desc* d) {
   if (d->out_y) GCB_CHECK_ARG(aligned16(d->out_y) && d->ld_out_y % 4 == 0 && d->ld_out_y >= d->n_valid, "out_y unaligned");
   if (d->residual) GCB_CHECK_ARG(aligned16(d->residual) && d->ld_res % 4 == 0, "residual unaligned");
   GCB_CHECK_ARG(d->act == GCB_ACT_NONE || d->act == GCB_ACT_SWISH, "unknown activation");
+  GCB_CHECK_ARG(d->n_pre_add >= 0 && d->n_pre_add <= 2, "n_pre_add must be 0..2");
+  if (d->n_pre_add > 0) {
+    GCB_CHECK_ARG(d->ln_scale == nullptr, "pre_add cannot be combined with LayerNorm");
+    GCB_CHECK_ARG(d->n_valid == d->n, "pre_add requires n_valid == n");
+    for (int i = 0; i < d->n_pre_add; ++i)
+      GCB_CHECK_ARG(d->pre_add[i].table != nullptr && aligned16(d->pre_add[i].table) &&
+                        d->pre_add[i].ld % 4 == 0 && d->pre_add[i].ld >= d->n,
+                    "pre_add table null/unaligned");
+  }
   if (d->precision == GCB_PREC_FP32_SIMT) {
     GCB_CHECK_ARG(d->w_f32 != nullptr, "w_f32 is null (FP32_SIMT)");
   } else {
@@ -220,15 +229,22 @@ gcb_segment seg(const float* table, const int32_t* idx, int ld, int k, int k_val
 
 // Two-layer MLP: hidden = swish(concat(segs) @ W0 + b0);  y = [LN](hidden @ W1 + b1).
 int run_mlp(StepCtx& c, const gcb_mlp& w, int rows, int nseg, const gcb_segment* segs,
-            const float* residual, float* out, int ld_out, float* out_y) {
+            const float* residual, float* out, int ld_out, float* out_y,
+            const void* w0_packed_override = nullptr, const float* w0_f32_override = nullptr,
+            int n_pre = 0, const gcb_pre_add* pre = nullptr) {
   if (rows == 0) return GCB_OK;
   gcb_layer_desc l0;
   memset(&l0, 0, sizeof(l0));
   l0.rows = rows; l0.n = 512; l0.n_valid = 512; l0.nseg = nseg;
   int k0 = 0;
   for (int s = 0; s < nseg; ++s) { l0.seg[s] = segs[s]; k0 += segs[s].k; }
-  if (k0 != w.k0) return fail(GCB_ERR_INVALID, "run_mlp: segment widths do not match the weight");
-  l0.w_packed = w.w0_packed; l0.w_f32 = w.w0_f32; l0.bias = w.b0;
+  if (w0_packed_override == nullptr && k0 != w.k0)
+    return fail(GCB_ERR_INVALID, "run_mlp: segment widths do not match the weight");
+  l0.w_packed = w0_packed_override ? w0_packed_override : w.w0_packed;
+  l0.w_f32 = w0_packed_override ? w0_f32_override : w.w0_f32;
+  l0.bias = w.b0;
+  l0.n_pre_add = n_pre;
+  for (int i = 0; i < n_pre; ++i) l0.pre_add[i] = pre[i];
   l0.act = GCB_ACT_SWISH;
   l0.out = c.m->hidden; l0.ld_out = 512;
   l0.precision = c.m->precision;
@@ -249,6 +265,49 @@ int run_mlp(StepCtx& c, const gcb_mlp& w, int rows, int nseg, const gcb_segment*
   if (rc) return rc;
   c.launches += 2;
   return GCB_OK;
+}
+
+// Node-level projection P = v @ W  (no bias, no activation): one [rows,512]x[512,512] layer.
+int run_projection(StepCtx& c, const void* w_packed, const float* w_f32, const float* v, int rows,
+                   float* out) {
+  if (rows == 0) return GCB_OK;
+  gcb_layer_desc l;
+  memset(&l, 0, sizeof(l));
+  l.rows = rows; l.n = 512; l.n_valid = 512; l.nseg = 1;
+  l.seg[0] = seg(v, nullptr, 512, 512, 512);
+  l.w_packed = w_packed; l.w_f32 = w_f32; l.bias = c.m->zero_bias;
+  l.act = GCB_ACT_NONE;
+  l.out = out; l.ld_out = 512;
+  l.precision = c.m->precision;
+  int rc = gcb_layer_forward(&l, c.stream);
+  if (rc) return rc;
+  c.launches += 1;
+  return GCB_OK;
+}
+
+// Edge MLP  LN.MLP([e | vs[snd] | vr[rcv]]).  With pregather the first layer is evaluated
+// as e @ W_e + (vs @ W_s)[snd] + (vr @ W_r)[rcv]: two node-level projections, then an edge
+// layer with K = 512 whose epilogue adds the gathered projections before the activation.
+int run_edge_mlp(StepCtx& c, const gcb_mlp& w, const gcb_mlp_split* split, int rows,
+                 const float* e, const float* vs, int n_s, const int32_t* snd, float* proj_s,
+                 const float* vr, int n_r, const int32_t* rcv, float* proj_r,
+                 const float* residual, float* out, float* out_y) {
+  const int D = 512;
+  gcb_segment s[3];
+  if (!c.m->pregather || split == nullptr) {
+    s[0] = seg(e, nullptr, D, D, D);
+    s[1] = seg(vs, snd, D, D, D);
+    s[2] = seg(vr, rcv, D, D, D);
+    return run_mlp(c, w, rows, 3, s, residual, out, D, out_y);
+  }
+  int rc;
+  if ((rc = run_projection(c, split->ws_packed, split->ws_f32, vs, n_s, proj_s))) return rc;
+  if ((rc = run_projection(c, split->wr_packed, split->wr_f32, vr, n_r, proj_r))) return rc;
+  gcb_pre_add pre[2];
+  pre[0].table = proj_s; pre[0].idx = snd; pre[0].ld = D; pre[0].pad_ = 0;
+  pre[1].table = proj_r; pre[1].idx = rcv; pre[1].ld = D; pre[1].pad_ = 0;
+  s[0] = seg(e, nullptr, D, D, D);
+  return run_mlp(c, w, rows, 1, s, residual, out, D, out_y, split->we_packed, split->we_f32, 2, pre);
 }
 
 }  // namespace
@@ -306,6 +365,7 @@ int gcb_layer_forward(const gcb_layer_desc* d, void* stream) {
     a_elems += static_cast<double>(d->seg[i].k_valid) * d->seg[i].fan;
   }
   const double rows = d->rows;
+  a_elems += static_cast<double>(d->n_pre_add) * d->n_valid;
   const double flops = 2.0 * rows * kv * d->n_valid;
   const double bytes = 4.0 * (rows * a_elems + kv * d->n_valid +
                               rows * d->n_valid * ((d->out ? 1 : 0) + (d->out_y ? 1 : 0) +
@@ -374,6 +434,9 @@ int gcb_forward(const gcb_model* m, const float* grid_in, float* grid_out, void*
   GCB_CHECK_ARG(m && grid_in && grid_out, "null pointer");
   GCB_CHECK_ARG(m->msg_steps >= 1 && m->msg_steps <= GCB_MAX_MSG_STEPS, "msg_steps out of range");
   GCB_CHECK_ARG(m->e_m2g == 3 * m->num_grid, "mesh2grid must have fan-in 3");
+  if (m->pregather)
+    GCB_CHECK_ARG(m->zero_bias && m->proj_grid && m->proj_mesh_a && m->proj_mesh_b,
+                  "pregather needs zero_bias and the proj_* buffers");
   StepCtx c{m, static_cast<cudaStream_t>(stream), 0};
   int rc;
   gcb_segment s[3];
@@ -390,10 +453,10 @@ int gcb_forward(const gcb_model* m, const float* grid_in, float* grid_out, void*
   s[0] = seg(m->g2m_feat, nullptr, 4, 16, 4);
   if ((rc = run_mlp(c, m->enc_e_g2m, m->e_g2m, 1, s, nullptr, m->edge_a, D, nullptr))) return rc;
   // m1 = LN.MLP([e1 | vg0[snd] | vm0[rcv]])  -> edge_b   (edge residual e1+m1 is dead)
-  s[0] = seg(m->edge_a, nullptr, D, D, D);
-  s[1] = seg(m->grid_lat, m->g2m_snd, D, D, D);
-  s[2] = seg(m->mesh_lat, m->g2m_rcv, D, D, D);
-  if ((rc = run_mlp(c, m->proc_e_g2m, m->e_g2m, 3, s, nullptr, m->edge_b, D, nullptr))) return rc;
+  if ((rc = run_edge_mlp(c, m->proc_e_g2m, &m->proc_e_g2m_split, m->e_g2m, m->edge_a,
+                         m->grid_lat, m->num_grid, m->g2m_snd, m->proj_grid,
+                         m->mesh_lat, m->num_mesh, m->g2m_rcv, m->proj_mesh_a,
+                         nullptr, m->edge_b, nullptr))) return rc;
   // agg1 = segment_sum(m1)
   if ((rc = gcb_segment_sum(m->edge_b, D, m->g2m_row_ptr, m->num_mesh, m->mesh_agg, D, D, stream))) return rc;
   c.launches += 1;
@@ -412,11 +475,11 @@ int gcb_forward(const gcb_model* m, const float* grid_in, float* grid_out, void*
     const bool last = (k == m->msg_steps - 1);
     // m = LN.MLP([e | v[snd] | v[rcv]]) -> mesh_msg;  e += m (skipped on the last
     // step: the updated edge latents are never read again).
-    s[0] = seg(m->mesh_edge, nullptr, D, D, D);
-    s[1] = seg(m->mesh_lat, m->mesh_snd, D, D, D);
-    s[2] = seg(m->mesh_lat, m->mesh_rcv, D, D, D);
-    if ((rc = run_mlp(c, m->proc_e_mesh[k], m->e_mesh, 3, s, last ? nullptr : m->mesh_edge,
-                      last ? nullptr : m->mesh_edge, D, m->mesh_msg))) return rc;
+    if ((rc = run_edge_mlp(c, m->proc_e_mesh[k], &m->proc_e_mesh_split[k], m->e_mesh, m->mesh_edge,
+                           m->mesh_lat, m->num_mesh, m->mesh_snd, m->proj_mesh_a,
+                           m->mesh_lat, m->num_mesh, m->mesh_rcv, m->proj_mesh_b,
+                           last ? nullptr : m->mesh_edge, last ? nullptr : m->mesh_edge,
+                           m->mesh_msg))) return rc;
     if ((rc = gcb_segment_sum(m->mesh_msg, D, m->mesh_row_ptr, m->num_mesh, m->mesh_agg, D, D, stream))) return rc;
     c.launches += 1;
     // v += LN.MLP([v | agg])
@@ -429,10 +492,10 @@ int gcb_forward(const gcb_model* m, const float* grid_in, float* grid_out, void*
   s[0] = seg(m->m2g_feat, nullptr, 4, 16, 4);
   if ((rc = run_mlp(c, m->enc_e_m2g, m->e_m2g, 1, s, nullptr, m->edge_a, D, nullptr))) return rc;
   // m3 = LN.MLP([e3 | v[snd] | vg1[rcv]]) -> edge_b
-  s[0] = seg(m->edge_a, nullptr, D, D, D);
-  s[1] = seg(m->mesh_lat, m->m2g_snd, D, D, D);
-  s[2] = seg(m->grid_lat, m->m2g_rcv, D, D, D);
-  if ((rc = run_mlp(c, m->proc_e_m2g, m->e_m2g, 3, s, nullptr, m->edge_b, D, nullptr))) return rc;
+  if ((rc = run_edge_mlp(c, m->proc_e_m2g, &m->proc_e_m2g_split, m->e_m2g, m->edge_a,
+                         m->mesh_lat, m->num_mesh, m->m2g_snd, m->proj_mesh_a,
+                         m->grid_lat, m->num_grid, m->m2g_rcv, m->proj_grid,
+                         nullptr, m->edge_b, nullptr))) return rc;
   // vg2 = vg1 + LN.MLP([vg1 | sum of the 3 incoming messages])  (in place)
   s[0] = seg(m->grid_lat, nullptr, D, D, D);
   s[1] = seg(m->edge_b, nullptr, D, D, D, /*fan=*/3);

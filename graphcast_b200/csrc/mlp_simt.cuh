@@ -79,6 +79,13 @@ mlp_layer_simt_kernel(const __grid_constant__ gcb_layer_desc d) {
       if (j < ncol) {
         const int c = tx + 64 * j;
         float x = acc[i][j] + d.bias[c];
+        const long long grow = row0 + ty * 8 + i;
+        if (grow < d.rows) {
+          for (int pa = 0; pa < d.n_pre_add; ++pa) {
+            const long long src = d.pre_add[pa].idx ? static_cast<long long>(d.pre_add[pa].idx[grow]) : grow;
+            x += d.pre_add[pa].table[src * d.pre_add[pa].ld + c];
+          }
+        }
         if (d.act == GCB_ACT_SWISH) x = swish_exact(x);
         ytile[(ty * 8 + i) * n + c] = x;
       }

@@ -45,18 +45,22 @@ constexpr int kALbo = kTileM * 16 + 64;           // 2112
 constexpr int kAPartBytes = 2 * kALbo;            // 4224: one of {hi, lo}
 constexpr int kEpiRowFloats = 36;                 // 32 + 4 pad: conflict-free 16 B accesses
 constexpr int kEpiStageBytes = 4 * 32 * kEpiRowFloats * 4;   // per-warp 32x32 transpose tiles
+// Pre-activation addend chunks (gathered node projections), double buffered:
+// [2][128 rows][36 floats], filled by producer group 1, read by the epilogue.
+constexpr int kGBufFloats = kTileM * kEpiRowFloats;
+constexpr int kGBytes = 2 * kGBufFloats * 4;
 constexpr int kMaxN = 512;
 constexpr int kMaxKSteps = 128;                   // K <= 2048
 constexpr int kTmemCols = 512;
 
 template <bool kSplit>
 struct TcConfig {
-  static constexpr int kStages = kSplit ? 5 : 8;
+  static constexpr int kStages = kSplit ? 4 : 8;
   static constexpr int kAStageBytes = kSplit ? 2 * kAPartBytes : kAPartBytes;
   static constexpr int kBStageBytes = kSplit ? kMaxN * kKStep * 4 : kMaxN * kKStep * 2;
   static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
   static constexpr int kParamBytes = 3 * kMaxN * 4;  // bias, ln scale, ln offset
-  static constexpr int kSmemBytes = kStages * kStageBytes + kParamBytes + kEpiStageBytes + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kParamBytes + kEpiStageBytes + kGBytes + 1024;
 };
 
 __device__ __forceinline__ float swish_f(float x) {
@@ -88,6 +92,11 @@ struct SegInfo {
   const int32_t* idx;
   int ld, k_valid, fan, pad;
 };
+struct PreAddInfo {
+  const float* table;
+  const int32_t* idx;
+  long long ld;
+};
 
 // kSplit: bf16x3 (hi/lo) vs single bf16 product.  kSwish / kLN: epilogue variant,
 // compile-time so the per-element loops are straight-line code.
@@ -101,14 +110,18 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
   float* s_scale = s_bias + kMaxN;
   float* s_offset = s_scale + kMaxN;
   float* s_epi = s_offset + kMaxN;                                  // [4][32][36]
-  uint8_t* tail = reinterpret_cast<uint8_t*>(s_epi + 4 * 32 * kEpiRowFloats);
+  float* s_g = s_epi + 4 * 32 * kEpiRowFloats;                      // [2][128][36]
+  uint8_t* tail = reinterpret_cast<uint8_t*>(s_g + 2 * kGBufFloats);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);          // [kStages]
   uint64_t* empty_bar = full_bar + Cfg::kStages;                   // [kStages]
   uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;              // [1]
   uint64_t* tmem_empty_bar = tmem_full_bar + 1;                    // [1]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
+  uint64_t* g_full_bar = tmem_empty_bar + 1;                       // [2]
+  uint64_t* g_empty_bar = g_full_bar + 2;                          // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(g_empty_bar + 2);
   SegInfo* s_seg = reinterpret_cast<SegInfo*>(tmem_base_slot + 2);        // [3]
-  KStepInfo* ks_info = reinterpret_cast<KStepInfo*>(s_seg + 3);           // [kMaxKSteps]
+  PreAddInfo* s_pre = reinterpret_cast<PreAddInfo*>(s_seg + 3);           // [2]
+  KStepInfo* ks_info = reinterpret_cast<KStepInfo*>(s_pre + 2);           // [kMaxKSteps]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -120,6 +133,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
   // Descriptor fields used inside hot loops, hoisted into registers once.
   const long long rows_total = d.rows;
   const int nseg = d.nseg;
+  const int n_pre = d.n_pre_add;               // gathered pre-activation addends (0..2)
   float* const out_ptr = d.out;
   float* const outy_ptr = d.out_y;
   const float* const res_ptr = d.residual;
@@ -147,6 +161,11 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
       s_seg[s].k_valid = d.seg[s].k_valid;
       s_seg[s].fan = d.seg[s].fan;
     }
+    for (int s = 0; s < n_pre; ++s) {
+      s_pre[s].table = d.pre_add[s].table;
+      s_pre[s].idx = d.pre_add[s].idx;
+      s_pre[s].ld = d.pre_add[s].ld;
+    }
     for (int s = 0; s < d.nseg; ++s)
       for (int k = 0; k < d.seg[s].k; k += kKStep) {
         ks_info[ks].seg = static_cast<uint8_t>(s);
@@ -159,6 +178,10 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
     }
     ptx::mbar_init(tmem_full_bar, 1);
     ptx::mbar_init(tmem_empty_bar, 4);   // 4 epilogue warps
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&g_full_bar[b], 4);   // 4 warps of producer group 1
+      ptx::mbar_init(&g_empty_bar[b], 4);  // 4 epilogue warps
+    }
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -253,7 +276,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
     float* my_epi = s_epi + ew * 32 * kEpiRowFloats;
     const int cg = lane & 7;                     // 16-byte column group inside the 32-col block
     const int rsub = lane >> 3;                  // row within a group of 4
-    uint32_t tile_iter = 0;
+    uint32_t tile_iter = 0, g_count = 0;
     for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles);
          base += tile_stride, ++tile_iter) {
       const long long row0 = static_cast<long long>(base + crank) * kTileM + ew * 32;
@@ -323,6 +346,21 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
             *reinterpret_cast<float4*>(&b[4 * q]) = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * q);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += b[j];
+        }
+        if (!kLN && n_pre > 0) {
+          // Add the gathered node projections staged by producer group 1.
+          const uint32_t gb = g_count & 1;
+          ptx::mbar_wait(&g_full_bar[gb], (g_count >> 1) & 1);
+          const float* gp = s_g + gb * kGBufFloats + (ew * 32 + lane) * kEpiRowFloats;
+          float g[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(&g[4 * q]) = *reinterpret_cast<const float4*>(gp + 4 * q);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += g[j];
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&g_empty_bar[gb]);
+          ++g_count;
         }
         if (kSwish) {
 #pragma unroll
@@ -397,6 +435,55 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
     const int sub = tid_g & 3;                    // which float4 of the 16-wide K-step
     const int rg = tid_g >> 2;                    // 0..31; rows rg + 32*i
     const uint32_t sts_off = (sub >> 1) * kALbo + (sub & 1) * 8;
+    const bool gather_mode = !kLN && n_pre > 0;
+    if (gather_mode && group == 1) {
+      // ===== pre-activation addend producer =====
+      // Thread (rp, cgp): rows rp + 16*p (p < 8), 16-byte column group cgp of each 32-column
+      // chunk: 8 lanes read one 128-byte line segment of a gathered row.
+      const int cgp = tid_g & 7, rp = tid_g >> 3;
+      uint32_t gc = 0;
+      for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles); base += tile_stride) {
+        const long long trow0 = static_cast<long long>(base + crank) * kTileM;
+        const float* p0[8];
+        const float* p1[8];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          const long long grow = trow0 + rp + 16 * p;
+          p0[p] = nullptr; p1[p] = nullptr;
+          if (grow < rows_total) {
+            const PreAddInfo a = s_pre[0];
+            p0[p] = a.table + (a.idx ? static_cast<long long>(__ldg(a.idx + grow)) : grow) * a.ld + cgp * 4;
+            if (n_pre > 1) {
+              const PreAddInfo b = s_pre[1];
+              p1[p] = b.table + (b.idx ? static_cast<long long>(__ldg(b.idx + grow)) : grow) * b.ld + cgp * 4;
+            }
+          }
+        }
+        for (int c0 = 0; c0 < n; c0 += 32, ++gc) {
+          const uint32_t gb = gc & 1;
+          float4 acc[8];
+#pragma unroll
+          for (int p = 0; p < 8; ++p)
+            acc[p] = p0[p] ? __ldg(reinterpret_cast<const float4*>(p0[p] + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (n_pre > 1) {
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+              if (p1[p]) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p1[p] + c0));
+                acc[p].x += t.x; acc[p].y += t.y; acc[p].z += t.z; acc[p].w += t.w;
+              }
+            }
+          }
+          ptx::mbar_wait(&g_empty_bar[gb], ((gc >> 1) & 1) ^ 1);
+          float* gdst = s_g + gb * kGBufFloats + rp * kEpiRowFloats + cgp * 4;
+#pragma unroll
+          for (int p = 0; p < 8; ++p)
+            *reinterpret_cast<float4*>(gdst + 16 * p * kEpiRowFloats) = acc[p];
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&g_full_bar[gb]);
+        }
+      }
+    } else {
     uint32_t it = 0;
     for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles); base += tile_stride) {
       const uint32_t tile = base + crank;          // may be past the end: all-zero dummy tile
@@ -421,7 +508,8 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
       // owned K-step are in flight while the current one is converted and stored.
       for (int ks = 0; ks <= ksteps; ++ks) {
         const uint32_t this_it = it + ks;
-        const bool mine = (ks < ksteps) && ((this_it & 1u) == static_cast<uint32_t>(group));
+        // Normal mode: the two groups alternate K-steps.  Gather mode: group 0 owns all.
+        const bool mine = (ks < ksteps) && (gather_mode || (this_it & 1u) == static_cast<uint32_t>(group));
         float4 nxt[4];
         if (mine) {
           const int s = ks_info[ks].seg;
@@ -469,6 +557,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
         }
       }
       it += ksteps;
+    }
     }
   }
 

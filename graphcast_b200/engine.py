@@ -46,7 +46,7 @@ class Engine:
   def __init__(self, static_graph: graph_lib.StaticGraph,
                params: Mapping[str, Mapping[str, np.ndarray]], *,
                c_in: int, n_out: int, msg_steps: int, precision: str = "bf16x3",
-               device: Optional[torch.device] = None):
+               device: Optional[torch.device] = None, pregather: bool = True):
     if precision not in _native.PRECISIONS:
       raise ValueError(f"unknown precision {precision!r}; expected one of "
                        f"{sorted(_native.PRECISIONS)}")
@@ -63,6 +63,9 @@ class Engine:
     self.n_out = n_out
     self.msg_steps = msg_steps
     self.precision = precision
+    # pregather: evaluate the first edge-MLP layer as  e@W_e + (v@W_s)[snd] + (v@W_r)[rcv]
+    # (node-level projections gathered in the epilogue) -- 30 % fewer tensor-core MACs.
+    self.pregather = bool(pregather)
     self.c_in_pad = _ceil(c_in + 3, 16)
     self.c_in_valid = _ceil(c_in + 3, 4)
     g = static_graph
@@ -121,6 +124,7 @@ class Engine:
     m.c_in_pad, m.c_in_valid = self.c_in_pad, self.c_in_valid
     m.msg_steps = self.msg_steps
     m.precision = _native.PRECISIONS[self.precision]
+    m.pregather = 1 if self.pregather else 0
 
   # -- weights ---------------------------------------------------------------------
   def _pack_linear(self, w: np.ndarray, seg_real, seg_pad, n_pad: int):
@@ -178,6 +182,20 @@ class Engine:
     mlp.k0, mlp.n1, mlp.n1_valid = k0, n1_pad, n1_real
     return mlp
 
+  def _make_split(self, params, stem: str) -> _native.MlpSplit:
+    """Row blocks [edge | sender | receiver] of a [1536,512] first edge-MLP layer
+    (concat order of the reference, typed_graph_net.py:637-638), each packed alone."""
+    w0 = np.asarray(params[f"{stem}_mlp/~/linear_0"]["w"], np.float32)
+    D = LATENT
+    if w0.shape != (3 * D, D):
+      raise ValueError(f"{stem}: expected a [{3 * D},{D}] first layer")
+    sp = _native.MlpSplit()
+    for name, block in (("we", w0[:D]), ("ws", w0[D:2 * D]), ("wr", w0[2 * D:])):
+      img, f32, _ = self._pack_linear(block, [D], [D], D)
+      setattr(sp, f"{name}_packed", self._ptr(img))
+      setattr(sp, f"{name}_f32", self._ptr(f32))
+    return sp
+
   def _upload_weights(self, params) -> None:
     m = self._model
     D = LATENT
@@ -200,6 +218,12 @@ class Engine:
     m.proc_e_m2g = mk(params, mlp_stem(g, "processor_edges_0_", "mesh2grid"), [D] * 3, [D] * 3, D, True)
     m.proc_n_grid_m2g = mk(params, mlp_stem(g, "processor_nodes_0_", "grid_nodes"), [D] * 2, [D] * 2, D, True)
     m.dec_grid = mk(params, mlp_stem(g, "decoder_nodes_", "grid_nodes"), [D], [D], self.n_out, False)
+    if self.pregather:
+      m.proc_e_g2m_split = self._make_split(params, mlp_stem("grid2mesh_gnn", "processor_edges_0_", "grid2mesh"))
+      m.proc_e_m2g_split = self._make_split(params, mlp_stem("mesh2grid_gnn", "processor_edges_0_", "mesh2grid"))
+      for k in range(self.msg_steps):
+        m.proc_e_mesh_split[k] = self._make_split(params, mlp_stem("mesh_gnn", f"processor_edges_{k}_", "mesh"))
+      m.zero_bias = self._ptr(self._dev(np.zeros([D], np.float32), torch.float32))
 
   # -- workspace ---------------------------------------------------------------------
   def _alloc_workspace(self) -> None:
@@ -214,6 +238,11 @@ class Engine:
     self.mesh_edge, self.mesh_msg = f(m.e_mesh, LATENT), f(m.e_mesh, LATENT)
     self.grid_in = f(m.num_grid, self.c_in_pad)
     self.grid_out = f(m.num_grid, 256)
+    if self.pregather:
+      self.proj_grid = f(m.num_grid, LATENT)
+      self.proj_mesh_a, self.proj_mesh_b = f(m.num_mesh, LATENT), f(m.num_mesh, LATENT)
+      m.proj_grid = self._ptr(self.proj_grid)
+      m.proj_mesh_a, m.proj_mesh_b = self._ptr(self.proj_mesh_a), self._ptr(self.proj_mesh_b)
     m.hidden, m.edge_a, m.edge_b = self._ptr(self.hidden), self._ptr(self.edge_a), self._ptr(self.edge_b)
     m.grid_lat, m.mesh_lat, m.mesh_agg = self._ptr(self.grid_lat), self._ptr(self.mesh_lat), self._ptr(self.mesh_agg)
     m.mesh_edge, m.mesh_msg = self._ptr(self.mesh_edge), self._ptr(self.mesh_msg)
@@ -221,6 +250,8 @@ class Engine:
   def workspace_bytes(self) -> int:
     ts = [self.hidden, self.edge_a, self.edge_b, self.grid_lat, self.mesh_lat, self.mesh_agg,
           self.mesh_edge, self.mesh_msg, self.grid_in, self.grid_out]
+    if self.pregather:
+      ts += [self.proj_grid, self.proj_mesh_a, self.proj_mesh_b]
     return sum(t.numel() * t.element_size() for t in ts)
 
   # -- execution ---------------------------------------------------------------------

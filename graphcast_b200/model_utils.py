@@ -187,6 +187,8 @@ def variable_to_planes(var: xs.DataArray, sizes: Mapping[str, int]):
            la if "lat" in var.dims else 1, lo if "lon" in var.dims else 1]
   arr = arr.reshape(shape)
   target = (sizes["batch"], nch, sizes["lat"], sizes["lon"])
+  if tuple(arr.shape) == target:
+    return arr
   if xs._is_torch(arr):
     return arr.expand(*target)
   return np.broadcast_to(arr, target)

@@ -63,9 +63,21 @@ typedef struct {
   int32_t fan;          /* >= 1 */
 } gcb_segment;
 
+/* A gathered pre-activation addend:  y_pre[r, :] += table[(idx ? idx[r] : r), 0:n].
+ * Used for the algebraically split first edge-MLP layer
+ *     [e | v_s | v_r] @ W  =  e @ W_e + (v @ W_s)[senders] + (v @ W_r)[receivers]
+ * where the node-level projections are computed once per node instead of per edge
+ * (the reference's newer DeepGNN does the same, utils/deep_gnn.py:106-108,245-260). */
+typedef struct {
+  const float* table;   /* [*, ld] fp32 */
+  const int32_t* idx;   /* [rows] gather index or NULL */
+  int32_t ld;
+  int32_t pad_;
+} gcb_pre_add;
+
 /* One fused linear layer over `rows` rows:
  *     z   = concat(segments)                         [rows, K],  K = sum k
- *     y   = act(z @ W + bias)                        [rows, n]
+ *     y   = act(z @ W + bias + sum_p pre_add_p)      [rows, n]
  *     y   = LayerNorm(y) * ln_scale + ln_offset      (if ln_scale != NULL; eps 1e-5)
  *     out_y[r] = y[r]                                (if out_y  != NULL)
  *     out[r]   = (residual ? residual[r] : 0) + y[r] (if out    != NULL)
@@ -89,6 +101,8 @@ typedef struct {
   float* out;   int32_t ld_out;
   float* out_y; int32_t ld_out_y;
   int32_t precision;    /* gcb_precision */
+  int32_t n_pre_add;    /* 0..2; requires ln_scale == NULL and n_valid % 32 == 0 */
+  gcb_pre_add pre_add[2];
 } gcb_layer_desc;
 
 int gcb_abi_version(void);
@@ -156,6 +170,13 @@ typedef struct {
   int32_t n1_valid;
 } gcb_mlp;
 
+/* Row blocks of a [1536,512] first edge-MLP layer, each packed as its own [512,512] layer. */
+typedef struct {
+  const void* we_packed; const float* we_f32;
+  const void* ws_packed; const float* ws_f32;
+  const void* wr_packed; const float* wr_f32;
+} gcb_mlp_split;
+
 #define GCB_MAX_MSG_STEPS 64
 
 /* Everything one forward step needs.  Edge arrays are in EXECUTION order
@@ -168,6 +189,7 @@ typedef struct {
   int32_t c_in_valid;     /* real width incl. the 3 structural features (mult. of 4 pad ok) */
   int32_t msg_steps;
   int32_t precision;
+  int32_t pregather;      /* 1: split first edge-MLP layers (needs the *_split weights + proj_*) */
 
   /* static graph */
   const int32_t* g2m_snd; const int32_t* g2m_rcv; const int32_t* g2m_row_ptr;
@@ -184,6 +206,15 @@ typedef struct {
   gcb_mlp proc_e_mesh[GCB_MAX_MSG_STEPS];
   gcb_mlp proc_n_mesh[GCB_MAX_MSG_STEPS];
   gcb_mlp enc_e_m2g, proc_e_m2g, proc_n_grid_m2g, dec_grid;
+
+  /* pregather only: first-layer weights of the four edge-MLP families split by rows
+   * into edge / sender / receiver blocks ([512,512] each; b0 stays in the MLP). */
+  gcb_mlp_split proc_e_g2m_split, proc_e_m2g_split;
+  gcb_mlp_split proc_e_mesh_split[GCB_MAX_MSG_STEPS];
+  const float* zero_bias;   /* [512] zeros */
+  float* proj_grid;         /* [num_grid, 512] */
+  float* proj_mesh_a;       /* [num_mesh, 512] */
+  float* proj_mesh_b;       /* [num_mesh, 512] */
 
   /* workspace (fp32): */
   float* hidden;      /* [max_rows, 512] */

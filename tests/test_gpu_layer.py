@@ -135,6 +135,42 @@ def test_ragged_row_counts(rows):
   assert err < TOL["bf16x3"], err
 
 
+@pytest.mark.parametrize("prec", ["fp32_simt", "bf16x3", "bf16"])
+@pytest.mark.parametrize("rows", [700, 128 * 148 + 77])
+def test_gathered_pre_activation_addends(prec, rows):
+  """Split first edge-MLP layer: swish(e @ W_e + b + P_s[snd] + P_r[rcv])."""
+  lib = _native.lib()
+  dev = torch.device("cuda:0")
+  g = torch.Generator().manual_seed(3)
+  e = torch.randn(rows, 512, generator=g)
+  ps, pr = torch.randn(301, 512, generator=g), torch.randn(97, 516, generator=g)
+  snd = torch.randint(0, 301, (rows,), generator=g, dtype=torch.int32)
+  rcv = torch.randint(0, 97, (rows,), generator=g, dtype=torch.int32)
+  w = torch.randn(512, 512, generator=g) / np.sqrt(512)
+  bias = 0.1 * torch.randn(512, generator=g)
+  img, wf = _pack(lib, w.numpy(), 512, 512, dev)
+  ed, psd, prd, sd, rd, bd = (t.to(dev) for t in (e, ps, pr, snd, rcv, bias))
+  out = torch.empty(rows, 512, device=dev)
+  d = _native.LayerDesc()
+  d.rows, d.n, d.n_valid, d.nseg = rows, 512, 512, 1
+  d.seg[0].table, d.seg[0].ld, d.seg[0].k, d.seg[0].k_valid, d.seg[0].fan = ed.data_ptr(), 512, 512, 512, 1
+  d.w_packed, d.w_f32, d.bias, d.act = img.data_ptr(), wf.data_ptr(), bd.data_ptr(), 1
+  d.out, d.ld_out = out.data_ptr(), 512
+  d.precision = _native.PRECISIONS[prec]
+  d.n_pre_add = 2
+  d.pre_add[0].table, d.pre_add[0].idx, d.pre_add[0].ld = psd.data_ptr(), sd.data_ptr(), 512
+  d.pre_add[1].table, d.pre_add[1].idx, d.pre_add[1].ld = prd.data_ptr(), rd.data_ptr(), 516
+  _native.check(lib.gcb_layer_forward(C.byref(d), torch.cuda.current_stream().cuda_stream), "layer")
+  torch.cuda.synchronize()
+  y = e.double() @ w.double() + bias.double() + ps.double()[snd.long()] + pr.double()[rcv.long(), :512]
+  want = y * torch.sigmoid(y)
+  err = float((out.cpu().double() - want).abs().max() / want.abs().max())
+  assert err < TOL[prec], err
+  # LayerNorm + pre_add is rejected
+  d.ln_scale, d.ln_offset = bd.data_ptr(), bd.data_ptr()
+  assert lib.gcb_layer_forward(C.byref(d), None) == -1
+
+
 def test_zero_rows_is_a_noop():
   lib = _native.lib()
   d = _native.LayerDesc()

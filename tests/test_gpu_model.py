@@ -21,15 +21,18 @@ def _rel(a, b):
   return float(np.abs(a - b).max() / np.abs(b).max())
 
 
+@pytest.mark.parametrize("pregather", [True, False])
 @pytest.mark.parametrize("prec,tol", [("bf16x3", 1e-4), ("fp32_simt", 1e-5), ("bf16", 5e-2)])
-def test_step_matches_oracle(prec, tol):
+def test_step_matches_oracle(prec, tol, pregather):
   g, params, x = _cases.small_case(c_in=31, n_out=23, msg_steps=3, batch=2)
   ref = oracle_gnn.Oracle(params, torch.float32).forward(g.as_dict(), x).numpy()
-  eng = engine.Engine(g, params, c_in=31, n_out=23, msg_steps=3, precision=prec)
+  eng = engine.Engine(g, params, c_in=31, n_out=23, msg_steps=3, precision=prec, pregather=pregather)
   y = eng.forward_features(torch.as_tensor(x)).cpu().numpy()
   assert np.isfinite(y).all()
   assert _rel(y, ref) <= tol
-  assert eng.launches_per_step == 2 * (6 + 1 + 2 * 3 + 4) + 1 + 3   # MLP layers + segment sums
+  mlp_layers = 2 * (6 + 1 + 2 * 3 + 4)
+  projections = 2 * (1 + 3 + 1) if pregather else 0       # two per edge MLP (g2m, 3 mesh steps, m2g)
+  assert eng.launches_per_step == mlp_layers + projections + 1 + 3   # + segment sums
 
 
 def test_stagewise_intermediates_match_oracle():
