@@ -289,6 +289,12 @@ def run_b200(args):
   ms_per_step = float(t.item()) / args.steps
   value = world * 1e3 / ms_per_step
 
+  if args.dump_launches and rank == 0:
+    with open(args.dump_launches, "w") as f:
+      f.write("idx,kind,ms,gflop,gbyte\n")
+      lo = (args.steps - 1) * per_step_launches
+      for i in range(lo, min(lo + per_step_launches, n_launch)):
+        f.write(f"{i - lo},{kinds[i]},{ms[i]:.4f},{flops[i] / 1e9:.2f},{nbytes[i] / 1e9:.4f}\n")
   # per-kind aggregation (this rank)
   kind_names = {0: "mlp_layer_tc", 1: "segment_sum", 2: "pack", 3: "unpack", 4: "mlp_layer_simt"}
   agg = {}
@@ -394,6 +400,7 @@ def main():
   ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=5)
   ap.add_argument("--skip-cpu-baseline", action="store_true")
   ap.add_argument("--cluster", type=int, default=0, help="CTAs per cluster (0 = library default)")
+  ap.add_argument("--dump-launches", default="", help="write per-launch (kind, ms, GFLOP, GB) of the last timed step to this file")
   ap.add_argument("--no-pregather", dest="pregather", action="store_false",
                   help="evaluate the first edge-MLP layer over the concatenated K=1536 input")
   args = ap.parse_args()

@@ -6,7 +6,7 @@ from graphcast_b200 import _native
 lib = _native.lib()
 dev = torch.device("cuda:0")
 
-def run(rows, k, n, ln, act, csize, out_y=False, residual=False, idx=False):
+def run(rows, k, n, ln, act, csize, out_y=False, residual=False, idx=False, pre=0):
   lib.gcb_set_cluster_size(csize)
   a = torch.randn(rows, k, device=dev)
   w = (torch.randn(k, n) / np.sqrt(k)).numpy().astype(np.float32)
@@ -27,6 +27,13 @@ def run(rows, k, n, ln, act, csize, out_y=False, residual=False, idx=False):
   if out_y: d.out_y, d.ld_out_y = oy.data_ptr(), 512
   if residual: d.residual, d.ld_res = res.data_ptr(), n
   d.precision = 0
+  if pre:
+    ptab = [torch.randn(40962, 512, device=dev) for _ in range(pre)]
+    pidx = [torch.sort(torch.randint(0, 40962, (rows,), dtype=torch.int32, device=dev))[0] if i else
+            torch.randint(0, 40962, (rows,), dtype=torch.int32, device=dev) for i in range(pre)]
+    d.n_pre_add = pre
+    for i in range(pre):
+      d.pre_add[i].table, d.pre_add[i].idx, d.pre_add[i].ld = ptab[i].data_ptr(), pidx[i].data_ptr(), 512
   tr = torch.zeros(64 * 8, dtype=torch.int64, device=dev)
   for _ in range(2):
     lib.gcb_layer_forward(C.byref(d), None)
@@ -38,7 +45,7 @@ def run(rows, k, n, ln, act, csize, out_y=False, residual=False, idx=False):
   lib.gcb_debug_trace(None)
   t = tr.cpu().numpy().reshape(64, 8)
   ntile = min(64, (rows + 127) // 128 // 148)
-  print(f"rows={rows} k={k} n={n} ln={ln} act={act} cluster={csize} out_y={out_y} res={residual} idx={idx}: {e0.elapsed_time(e1):.3f} ms; tiles/CTA~{ntile}")
+  print(f"rows={rows} k={k} n={n} ln={ln} act={act} cluster={csize} out_y={out_y} res={residual} idx={idx} pre={pre}: {e0.elapsed_time(e1):.3f} ms; tiles/CTA~{ntile}")
   base = t[1, 0]
   for i in range(1, min(ntile, 6)):
     r = t[i]
@@ -47,8 +54,9 @@ def run(rows, k, n, ln, act, csize, out_y=False, residual=False, idx=False):
           f"next_acc_free+{t[i+1,0]-r[5]:6d}  tile_total={t[i+1,0]-r[0]}")
 
 rows = 148 * 128 * 8
-for cs in (1, 2):
-  run(rows, 16, 512, False, True, cs)
-  run(rows, 512, 512, True, False, cs)
+for cs in (2,):
+  run(rows, 512, 512, False, True, cs)
+  run(rows, 512, 512, False, True, cs, pre=2)
+  run(rows, 512, 512, False, False, cs)
   run(rows, 512, 512, True, False, cs, out_y=True, residual=True)
   run(rows, 1536, 512, False, True, cs, idx=True)
