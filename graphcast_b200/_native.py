@@ -39,7 +39,8 @@ class LayerDesc(C.Structure):
               ("residual", _fp), ("ld_res", C.c_int32),
               ("out", _fp), ("ld_out", C.c_int32),
               ("out_y", _fp), ("ld_out_y", C.c_int32),
-              ("precision", C.c_int32), ("n_pre_add", C.c_int32), ("pre_add", PreAdd * 2)]
+              ("precision", C.c_int32), ("n_pre_add", C.c_int32), ("pre_add", PreAdd * 2),
+              ("a_img", _fp), ("a_img_k", C.c_int32), ("out_img", _fp)]
 
 
 class MlpSplit(C.Structure):
@@ -84,6 +85,7 @@ EXPORTS = {
     "gcb_last_error": (C.c_char_p, []),
     "gcb_sm_count": (C.c_int, [C.c_int]),
     "gcb_packed_weight_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "gcb_a_image_bytes": (C.c_int64, [C.c_int64, C.c_int32]),
     "gcb_pack_weight_host": (C.c_int, [_fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _fp]),
     "gcb_layer_forward": (C.c_int, [C.POINTER(LayerDesc), _fp]),
     "gcb_segment_sum": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, _fp, C.c_int32, C.c_int32, _fp]),

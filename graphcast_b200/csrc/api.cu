@@ -107,9 +107,18 @@ int validate_layer(const gcb_layer_desc* d) {
   GCB_CHECK_ARG(d->rows >= 0, "rows < 0");
   GCB_CHECK_ARG(d->n == 256 || d->n == 512, "n must be 256 or 512");
   GCB_CHECK_ARG(d->n_valid > 0 && d->n_valid <= d->n, "n_valid out of range");
-  GCB_CHECK_ARG(d->nseg >= 1 && d->nseg <= 3, "nseg must be 1..3");
+  if (d->a_img != nullptr) {
+    GCB_CHECK_ARG(aligned16(d->a_img), "a_img unaligned");
+    GCB_CHECK_ARG(d->a_img_k > 0 && d->a_img_k % 16 == 0 && d->a_img_k / 16 <= gcb::kMaxKSteps,
+                  "a_img_k must be a positive multiple of 16");
+  } else {
+    GCB_CHECK_ARG(d->nseg >= 1 && d->nseg <= 3, "nseg must be 1..3");
+  }
+  if (d->out_img != nullptr)
+    GCB_CHECK_ARG(aligned16(d->out_img) && d->n == 512 && d->n_valid == 512,
+                  "out_img requires n = n_valid = 512");
   int ksteps = 0;
-  for (int s = 0; s < d->nseg; ++s) {
+  for (int s = 0; s < d->nseg && d->a_img == nullptr; ++s) {
     const gcb_segment& g = d->seg[s];
     GCB_CHECK_ARG(g.table != nullptr && aligned16(g.table), "segment table null/unaligned");
     GCB_CHECK_ARG(g.k > 0 && g.k % 16 == 0, "segment k must be a positive multiple of 16");
@@ -122,7 +131,7 @@ int validate_layer(const gcb_layer_desc* d) {
   GCB_CHECK_ARG(ksteps <= gcb::kMaxKSteps, "K too large");
   GCB_CHECK_ARG(d->bias != nullptr, "bias is null");
   GCB_CHECK_ARG((d->ln_scale == nullptr) == (d->ln_offset == nullptr), "ln_scale/ln_offset mismatch");
-  GCB_CHECK_ARG(d->out != nullptr || d->out_y != nullptr, "no output");
+  GCB_CHECK_ARG(d->out != nullptr || d->out_y != nullptr || d->out_img != nullptr, "no output");
   if (d->out) GCB_CHECK_ARG(aligned16(d->out) && d->ld_out % 4 == 0 && d->ld_out >= d->n_valid, "out unaligned");
   if (d->out_y) GCB_CHECK_ARG(aligned16(d->out_y) && d->ld_out_y % 4 == 0 && d->ld_out_y >= d->n_valid, "out_y unaligned");
   if (d->residual) GCB_CHECK_ARG(aligned16(d->residual) && d->ld_res % 4 == 0, "residual unaligned");
@@ -246,14 +255,14 @@ int run_mlp(StepCtx& c, const gcb_mlp& w, int rows, int nseg, const gcb_segment*
   l0.n_pre_add = n_pre;
   for (int i = 0; i < n_pre; ++i) l0.pre_add[i] = pre[i];
   l0.act = GCB_ACT_SWISH;
-  l0.out = c.m->hidden; l0.ld_out = 512;
+  l0.out_img = c.m->hidden;          // hidden activations go straight to operand-image form
   l0.precision = c.m->precision;
   int rc = gcb_layer_forward(&l0, c.stream);
   if (rc) return rc;
   gcb_layer_desc l1;
   memset(&l1, 0, sizeof(l1));
-  l1.rows = rows; l1.n = w.n1; l1.n_valid = w.n1_valid; l1.nseg = 1;
-  l1.seg[0] = seg(c.m->hidden, nullptr, 512, 512, 512);
+  l1.rows = rows; l1.n = w.n1; l1.n_valid = w.n1_valid; l1.nseg = 0;
+  l1.a_img = c.m->hidden; l1.a_img_k = 512;
   l1.w_packed = w.w1_packed; l1.w_f32 = w.w1_f32; l1.bias = w.b1;
   l1.ln_scale = w.ln_scale; l1.ln_offset = w.ln_offset;
   l1.act = GCB_ACT_NONE;
@@ -324,6 +333,12 @@ int gcb_sm_count(int device) {
   return n;
 }
 
+int64_t gcb_a_image_bytes(int64_t rows, int32_t k) {
+  if (rows < 0 || k <= 0 || k % 16 != 0) return -1;
+  const int64_t tiles = (rows + gcb::kTileM - 1) / gcb::kTileM;
+  return tiles * (k / 16) * GCB_A_IMAGE_BLOCK;
+}
+
 int64_t gcb_packed_weight_bytes(int32_t k, int32_t n) {
   if (k <= 0 || n <= 0 || k % 16 != 0) return -1;
   return static_cast<int64_t>(k) * n * 4;   // bf16 hi + bf16 lo per element
@@ -360,16 +375,17 @@ int gcb_layer_forward(const gcb_layer_desc* d, void* stream) {
   if (d->rows == 0) return GCB_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double kv = 0, a_elems = 0;
-  for (int i = 0; i < d->nseg; ++i) {
+  for (int i = 0; i < d->nseg && d->a_img == nullptr; ++i) {
     kv += d->seg[i].k_valid;
     a_elems += static_cast<double>(d->seg[i].k_valid) * d->seg[i].fan;
   }
+  if (d->a_img != nullptr) { kv = d->a_img_k; a_elems = d->a_img_k; }
   const double rows = d->rows;
   a_elems += static_cast<double>(d->n_pre_add) * d->n_valid;
   const double flops = 2.0 * rows * kv * d->n_valid;
   const double bytes = 4.0 * (rows * a_elems + kv * d->n_valid +
                               rows * d->n_valid * ((d->out ? 1 : 0) + (d->out_y ? 1 : 0) +
-                                                   (d->residual ? 1 : 0)));
+                                                   (d->residual ? 1 : 0) + (d->out_img ? 1 : 0)));
   ProfScope prof(st, d->precision == GCB_PREC_FP32_SIMT ? GCB_KIND_LAYER_SIMT : GCB_KIND_LAYER_TC,
                  flops, bytes);
   switch (d->precision) {

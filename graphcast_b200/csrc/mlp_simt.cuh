@@ -3,9 +3,22 @@
 // swish, LayerNorm, residual), exact fp32 FFMA arithmetic.  It exists to
 // validate the tcgen05 path on the device; it is not a performance path.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "../../include/graphcast_b200.h"
 
 namespace gcb {
+
+// Element (row, col) of an operand image (see gcb_layer_desc.a_img): byte offset of its
+// bf16 "hi" part; the "lo" part is 4224 bytes further.
+__device__ __forceinline__ size_t a_image_offset(long long row, int col, int k) {
+  const long long tile = row >> 7;
+  const int r = static_cast<int>(row & 127), ks = col >> 4, c = (col >> 3) & 1, j = col & 7;
+  return (static_cast<size_t>(tile) * (k >> 4) + ks) * GCB_A_IMAGE_BLOCK + c * 2112 + r * 16 + j * 2;
+}
+__device__ __forceinline__ float bf16_bits_to_float(unsigned short h) {
+  return __uint_as_float(static_cast<unsigned int>(h) << 16);
+}
 
 constexpr int kSimtRows = 32;
 constexpr int kSimtThreads = 256;
@@ -34,8 +47,10 @@ mlp_layer_simt_kernel(const __grid_constant__ gcb_layer_desc d) {
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
   int kglobal = 0;
-  for (int s = 0; s < d.nseg; ++s) {
-    const gcb_segment sg = d.seg[s];
+  const int nseg_eff = d.a_img ? 1 : d.nseg;
+  for (int s = 0; s < nseg_eff; ++s) {
+    gcb_segment sg = d.seg[s];
+    if (d.a_img) { sg.k = d.a_img_k; sg.k_valid = d.a_img_k; sg.fan = 1; sg.idx = nullptr; }
     for (int k0 = 0; k0 < sg.k; k0 += kSimtK, kglobal += kSimtK) {
       // A tile: 32 rows x 16 -> 512 elements, 2 per thread.
       for (int e = tid; e < kSimtRows * kSimtK; e += kSimtThreads) {
@@ -43,9 +58,16 @@ mlp_layer_simt_kernel(const __grid_constant__ gcb_layer_desc d) {
         const long long grow = row0 + r;
         float v = 0.f;
         if (grow < d.rows && (k0 + kk) < sg.k_valid) {
-          const long long src = sg.idx ? static_cast<long long>(sg.idx[grow]) : grow;
-          for (int j = 0; j < sg.fan; ++j)
-            v += sg.table[(src * sg.fan + j) * sg.ld + k0 + kk];
+          if (d.a_img) {
+            const unsigned char* p = static_cast<const unsigned char*>(d.a_img) +
+                                     a_image_offset(grow, k0 + kk, d.a_img_k);
+            v = bf16_bits_to_float(*reinterpret_cast<const unsigned short*>(p)) +
+                bf16_bits_to_float(*reinterpret_cast<const unsigned short*>(p + 4224));
+          } else {
+            const long long src = sg.idx ? static_cast<long long>(sg.idx[grow]) : grow;
+            for (int j = 0; j < sg.fan; ++j)
+              v += sg.table[(src * sg.fan + j) * sg.ld + k0 + kk];
+          }
         }
         a_tile[r * 17 + kk] = v;
       }
@@ -114,6 +136,13 @@ mlp_layer_simt_kernel(const __grid_constant__ gcb_layer_desc d) {
     for (int c = lane; c < nv; c += 32) {
       float x = ytile[r * n + c];
       if (d.ln_scale) x = (x - mean) * rstd * d.ln_scale[c] + d.ln_offset[c];
+      if (d.out_img) {
+        unsigned char* p = static_cast<unsigned char*>(d.out_img) + a_image_offset(grow, c, n);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+        *reinterpret_cast<__nv_bfloat16*>(p) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(p + 4224) = lo;
+      }
       if (d.out_y) d.out_y[grow * d.ld_out_y + c] = x;
       if (d.out) d.out[grow * d.ld_out + c] = x + (d.residual ? d.residual[grow * d.ld_res + c] : 0.f);
     }

@@ -52,6 +52,7 @@ constexpr int kGBytes = 2 * kGBufFloats * 4;
 constexpr int kMaxN = 512;
 constexpr int kMaxKSteps = 128;                   // K <= 2048
 constexpr int kTmemCols = 512;
+static_assert(2 * kAPartBytes == GCB_A_IMAGE_BLOCK, "A image block must match the stage layout");
 
 template <bool kSplit>
 struct TcConfig {
@@ -127,8 +128,16 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
   const int lane = threadIdx.x & 31;
   const int n = d.n;
   const int num_tiles = (d.rows + kTileM - 1) / kTileM;
+  // Operand-image input: A tiles arrive by TMA bulk copy instead of the gather warps.
+  const uint8_t* const a_img = static_cast<const uint8_t*>(d.a_img);
+  const bool a_is_img = a_img != nullptr;
   int ksteps = 0;
-  for (int s = 0; s < d.nseg; ++s) ksteps += d.seg[s].k / kKStep;
+  if (a_is_img) {
+    ksteps = d.a_img_k / kKStep;
+  } else {
+    for (int s = 0; s < d.nseg; ++s) ksteps += d.seg[s].k / kKStep;
+  }
+  uint8_t* const out_img = static_cast<uint8_t*>(d.out_img);
   constexpr bool has_ln = kLN;
   // Descriptor fields used inside hot loops, hoisted into registers once.
   const long long rows_total = d.rows;
@@ -166,14 +175,15 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
       s_pre[s].idx = d.pre_add[s].idx;
       s_pre[s].ld = d.pre_add[s].ld;
     }
-    for (int s = 0; s < d.nseg; ++s)
+    for (int s = 0; s < d.nseg && !a_is_img; ++s)
       for (int k = 0; k < d.seg[s].k; k += kKStep) {
         ks_info[ks].seg = static_cast<uint8_t>(s);
         ks_info[ks].koff = static_cast<uint16_t>(k);
         ++ks;
       }
     for (int s = 0; s < Cfg::kStages; ++s) {
-      ptx::mbar_init(&full_bar[s], 5);   // 1 weight producer + 4 activation warps
+      // 1 TMA lane (+ 4 activation-producer warps unless A comes from an image)
+      ptx::mbar_init(&full_bar[s], a_is_img ? 1 : 5);
       ptx::mbar_init(&empty_bar[s], csize);  // tcgen05.commit of every CTA in the cluster
     }
     ptx::mbar_init(tmem_full_bar, 1);
@@ -202,13 +212,21 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
       const size_t b_stride = static_cast<size_t>(n) * kKStep * 4;  // image always holds hi|lo
       const uint8_t* wimg = static_cast<const uint8_t*>(d.w_packed);
       const uint32_t slice = b_bytes / csize;
+      const uint32_t a_bytes = Cfg::kAStageBytes;            // hi (| lo) block of one K-step
       uint32_t it = 0;
       for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles); base += tile_stride) {
+        const uint32_t tile = base + crank;
+        const bool a_copy = a_is_img && tile < static_cast<uint32_t>(num_tiles);
+        const uint8_t* a_src = a_img + static_cast<size_t>(tile) * ksteps * GCB_A_IMAGE_BLOCK;
         for (int ks = 0; ks < ksteps; ++ks, ++it) {
           const uint32_t stage = it % Cfg::kStages;
           const uint32_t phase = (it / Cfg::kStages) & 1;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);     // free in every CTA of the cluster
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], b_bytes);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], b_bytes + (a_copy ? a_bytes : 0u));
+          if (a_copy)
+            ptx::bulk_g2s(stage_base + stage * Cfg::kStageBytes,
+                          a_src + static_cast<size_t>(ks) * GCB_A_IMAGE_BLOCK, a_bytes,
+                          &full_bar[stage]);
           uint8_t* dst = stage_base + stage * Cfg::kStageBytes + Cfg::kAStageBytes;
           const uint8_t* src = wimg + ks * b_stride;
           if (csize == 1) {
@@ -379,49 +397,70 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += g[j];
         }
+        if (out_img != nullptr && (base + crank) < static_cast<uint32_t>(num_tiles)) {
+          // Operand image of this tile for the next layer: thread = row, so the 16-byte
+          // pieces of 32 consecutive rows are contiguous -> 512-byte coalesced warp stores.
+          uint8_t* blk = out_img + (static_cast<size_t>(base + crank) * (n >> 4) + (c0 >> 4)) * GCB_A_IMAGE_BLOCK +
+                         (ew * 32 + lane) * 16;
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(my_epi + lane * kEpiRowFloats + q * 4) =
-              make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        __syncwarp();
-        if (fast) {
-          float4 y[8];
+          for (int ks2 = 0; ks2 < 2; ++ks2) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            y[i] = *reinterpret_cast<const float4*>(my_epi + (rsub + 4 * i) * kEpiRowFloats + cg * 4);
-          if (outy_ptr != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              *reinterpret_cast<float4*>(outy_ptr + (row0 + rsub + 4 * i) * ld_outy + col) = y[i];
-          }
-          if (out_ptr != nullptr) {
-            if (res_ptr != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                y[i].x += rr[i].x; y[i].y += rr[i].y; y[i].z += rr[i].z; y[i].w += rr[i].w;
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              *reinterpret_cast<float4*>(out_ptr + (row0 + rsub + 4 * i) * ld_out + col) = y[i];
-          }
-        } else {
-          // Ragged edge (last rows of the matrix / last partial column block).
-          for (int i = 0; i < 8; ++i) {
-            const int r = rsub + 4 * i;
-            const long long grow = row0 + r;
-            if (grow < rows_total) {
-              for (int e = 0; e < 4 && col + e < n_valid; ++e) {
-                const float yv = my_epi[r * kEpiRowFloats + cg * 4 + e];
-                if (outy_ptr != nullptr) outy_ptr[grow * ld_outy + col + e] = yv;
-                if (out_ptr != nullptr)
-                  out_ptr[grow * ld_out + col + e] =
-                      yv + (res_ptr ? res_ptr[grow * ld_res + col + e] : 0.f);
-              }
+            for (int c = 0; c < 2; ++c) {
+              const float* x = &v[ks2 * 16 + c * 8];
+              uint2 h0, l0, h1, l1;
+              ptx::split_bf16x4(make_float4(x[0], x[1], x[2], x[3]), h0, l0);
+              ptx::split_bf16x4(make_float4(x[4], x[5], x[6], x[7]), h1, l1);
+              uint8_t* dst = blk + ks2 * GCB_A_IMAGE_BLOCK + c * kALbo;
+              *reinterpret_cast<uint4*>(dst) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+              *reinterpret_cast<uint4*>(dst + kAPartBytes) = make_uint4(l0.x, l0.y, l1.x, l1.y);
             }
           }
         }
-        __syncwarp();
+        if (out_ptr != nullptr || outy_ptr != nullptr) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(my_epi + lane * kEpiRowFloats + q * 4) =
+                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          __syncwarp();
+          if (fast) {
+            float4 y[8];
+  #pragma unroll
+            for (int i = 0; i < 8; ++i)
+              y[i] = *reinterpret_cast<const float4*>(my_epi + (rsub + 4 * i) * kEpiRowFloats + cg * 4);
+            if (outy_ptr != nullptr) {
+  #pragma unroll
+              for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(outy_ptr + (row0 + rsub + 4 * i) * ld_outy + col) = y[i];
+            }
+            if (out_ptr != nullptr) {
+              if (res_ptr != nullptr) {
+  #pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  y[i].x += rr[i].x; y[i].y += rr[i].y; y[i].z += rr[i].z; y[i].w += rr[i].w;
+                }
+              }
+  #pragma unroll
+              for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(out_ptr + (row0 + rsub + 4 * i) * ld_out + col) = y[i];
+            }
+          } else {
+            // Ragged edge (last rows of the matrix / last partial column block).
+            for (int i = 0; i < 8; ++i) {
+              const int r = rsub + 4 * i;
+              const long long grow = row0 + r;
+              if (grow < rows_total) {
+                for (int e = 0; e < 4 && col + e < n_valid; ++e) {
+                  const float yv = my_epi[r * kEpiRowFloats + cg * 4 + e];
+                  if (outy_ptr != nullptr) outy_ptr[grow * ld_outy + col + e] = yv;
+                  if (out_ptr != nullptr)
+                    out_ptr[grow * ld_out + col + e] =
+                        yv + (res_ptr ? res_ptr[grow * ld_res + col + e] : 0.f);
+                }
+              }
+            }
+          }
+    __syncwarp();
+        }
       }
       if (ew == 0 && lane == 0) trace(tile_iter, 5);
       ptx::tc_fence_before_sync();
@@ -436,7 +475,9 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
     const int rg = tid_g >> 2;                    // 0..31; rows rg + 32*i
     const uint32_t sts_off = (sub >> 1) * kALbo + (sub & 1) * 8;
     const bool gather_mode = !kLN && n_pre > 0;
-    if (gather_mode && group == 1) {
+    // With an image-fed A operand both groups gather (alternating chunks, one buffer
+    // each); otherwise group 0 produces A and group 1 gathers.
+    if (gather_mode && (a_is_img || group == 1)) {
       // ===== pre-activation addend producer =====
       // Thread (rp, cgp): rows rp + 16*p (p < 8), 16-byte column group cgp of each 32-column
       // chunk: 8 lanes read one 128-byte line segment of a gathered row.
@@ -461,6 +502,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
         }
         for (int c0 = 0; c0 < n; c0 += 32, ++gc) {
           const uint32_t gb = gc & 1;
+          if (a_is_img && gb != static_cast<uint32_t>(group)) continue;
           float4 acc[8];
 #pragma unroll
           for (int p = 0; p < 8; ++p)
@@ -483,7 +525,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
           if (lane == 0) ptx::mbar_arrive(&g_full_bar[gb]);
         }
       }
-    } else {
+    } else if (!a_is_img) {
     uint32_t it = 0;
     for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles); base += tile_stride) {
       const uint32_t tile = base + crank;          // may be past the end: all-zero dummy tile

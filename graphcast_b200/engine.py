@@ -231,7 +231,8 @@ class Engine:
     f = lambda rows, cols: torch.empty([max(rows, 1), cols], dtype=torch.float32, device=self.device)
     max_rows = max(m.num_grid, m.num_mesh, m.e_g2m, m.e_mesh, m.e_m2g)
     big_edges = max(m.e_g2m, m.e_m2g)
-    self.hidden = f(max_rows, LATENT)
+    self.hidden = torch.empty([self._lib.gcb_a_image_bytes(max(max_rows, 1), LATENT)],
+                              dtype=torch.uint8, device=self.device)   # operand image
     self.edge_a, self.edge_b = f(big_edges, LATENT), f(big_edges, LATENT)
     self.grid_lat, self.mesh_lat = f(m.num_grid, LATENT), f(m.num_mesh, LATENT)
     self.mesh_agg = f(m.num_mesh, LATENT)

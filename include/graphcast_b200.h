@@ -103,7 +103,21 @@ typedef struct {
   int32_t precision;    /* gcb_precision */
   int32_t n_pre_add;    /* 0..2; requires ln_scale == NULL and n_valid % 32 == 0 */
   gcb_pre_add pre_add[2];
+  /* Operand-image path.  An "A image" of a [rows, 512] fp32 matrix is its bf16 hi/lo
+   * split stored tile by tile in the exact shared-memory layout of the tensor-core A
+   * operand: for row tile t (128 rows) and K-step s (16 columns) a block of
+   * GCB_A_IMAGE_BLOCK bytes = [hi: 2 chunks x (128 rows x 16 B) with a 64 B skew | lo: same].
+   *   a_img   != NULL : the layer input is this image (segments ignored, K = a_img_k);
+   *                     it is streamed by TMA bulk copies -- no gather / conversion warps.
+   *   out_img != NULL : the layer output y (n = n_valid = 512) is ALSO written as an image,
+   *                     ready to be the a_img of the next layer.
+   * gcb_a_image_bytes(rows, k) gives the buffer size. */
+  const void* a_img; int32_t a_img_k;
+  void* out_img;
 } gcb_layer_desc;
+
+#define GCB_A_IMAGE_BLOCK 8448
+int64_t gcb_a_image_bytes(int64_t rows, int32_t k);
 
 int gcb_abi_version(void);
 const char* gcb_last_error(void);
@@ -217,7 +231,7 @@ typedef struct {
   float* proj_mesh_b;       /* [num_mesh, 512] */
 
   /* workspace (fp32): */
-  float* hidden;      /* [max_rows, 512] */
+  void* hidden;       /* A image of [max_rows, 512] (gcb_a_image_bytes) */
   float* edge_a;      /* [max(e_g2m,e_m2g), 512] */
   float* edge_b;      /* [max(e_g2m,e_m2g), 512] */
   float* grid_lat;    /* [num_grid, 512] latent grid nodes */

@@ -171,6 +171,50 @@ def test_gathered_pre_activation_addends(prec, rows):
   assert lib.gcb_layer_forward(C.byref(d), None) == -1
 
 
+@pytest.mark.parametrize("prec", ["fp32_simt", "bf16x3", "bf16"])
+@pytest.mark.parametrize("rows", [1, 333, 128 * 148 * 2 + 5])
+def test_operand_image_chain(prec, rows):
+  """Two-layer MLP with the hidden activations handed over as an operand image:
+  layer 0 writes out_img, layer 1 reads a_img (TMA-fed A operand, no gather warps)."""
+  lib = _native.lib()
+  dev = torch.device("cuda:0")
+  g = torch.Generator().manual_seed(5)
+  x = torch.randn(rows, 512, generator=g)
+  w0 = torch.randn(512, 512, generator=g) / np.sqrt(512)
+  w1 = torch.randn(512, 512, generator=g) / np.sqrt(512)
+  b0, b1 = 0.1 * torch.randn(512, generator=g), 0.1 * torch.randn(512, generator=g)
+  sc, of = 1 + 0.1 * torch.randn(512, generator=g), 0.1 * torch.randn(512, generator=g)
+  img0, wf0 = _pack(lib, w0.numpy(), 512, 512, dev)
+  img1, wf1 = _pack(lib, w1.numpy(), 512, 512, dev)
+  xd, b0d, b1d, scd, ofd = (t.to(dev) for t in (x, b0, b1, sc, of))
+  nbytes = lib.gcb_a_image_bytes(rows, 512)
+  assert nbytes == ((rows + 127) // 128) * 32 * 8448
+  himg = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+  out = torch.empty(rows, 512, device=dev)
+  st = torch.cuda.current_stream().cuda_stream
+  d = _native.LayerDesc()
+  d.rows, d.n, d.n_valid, d.nseg = rows, 512, 512, 1
+  d.seg[0].table, d.seg[0].ld, d.seg[0].k, d.seg[0].k_valid, d.seg[0].fan = xd.data_ptr(), 512, 512, 512, 1
+  d.w_packed, d.w_f32, d.bias, d.act = img0.data_ptr(), wf0.data_ptr(), b0d.data_ptr(), 1
+  d.out_img = himg.data_ptr()
+  d.precision = _native.PRECISIONS[prec]
+  _native.check(lib.gcb_layer_forward(C.byref(d), st), "layer0")
+  d1 = _native.LayerDesc()
+  d1.rows, d1.n, d1.n_valid, d1.nseg = rows, 512, 512, 0
+  d1.a_img, d1.a_img_k = himg.data_ptr(), 512
+  d1.w_packed, d1.w_f32, d1.bias = img1.data_ptr(), wf1.data_ptr(), b1d.data_ptr()
+  d1.ln_scale, d1.ln_offset = scd.data_ptr(), ofd.data_ptr()
+  d1.out, d1.ld_out = out.data_ptr(), 512
+  d1.precision = _native.PRECISIONS[prec]
+  _native.check(lib.gcb_layer_forward(C.byref(d1), st), "layer1")
+  torch.cuda.synchronize()
+  h = x.double() @ w0.double() + b0.double()
+  h = h * torch.sigmoid(h)
+  y = torch.nn.functional.layer_norm(h @ w1.double() + b1.double(), (512,), sc.double(), of.double(), 1e-5)
+  err = float((out.cpu().double() - y).abs().max() / y.abs().max())
+  assert err < 2 * TOL[prec], err
+
+
 def test_zero_rows_is_a_noop():
   lib = _native.lib()
   d = _native.LayerDesc()

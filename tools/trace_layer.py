@@ -6,7 +6,7 @@ from graphcast_b200 import _native
 lib = _native.lib()
 dev = torch.device("cuda:0")
 
-def run(rows, k, n, ln, act, csize, out_y=False, residual=False, idx=False, pre=0):
+def run(rows, k, n, ln, act, csize, out_y=False, residual=False, idx=False, pre=0, img_in=False, img_out=False):
   lib.gcb_set_cluster_size(csize)
   a = torch.randn(rows, k, device=dev)
   w = (torch.randn(k, n) / np.sqrt(k)).numpy().astype(np.float32)
@@ -27,6 +27,12 @@ def run(rows, k, n, ln, act, csize, out_y=False, residual=False, idx=False, pre=
   if out_y: d.out_y, d.ld_out_y = oy.data_ptr(), 512
   if residual: d.residual, d.ld_res = res.data_ptr(), n
   d.precision = 0
+  if img_in:
+    ai = torch.zeros(lib.gcb_a_image_bytes(rows, k), dtype=torch.uint8, device=dev)
+    d.a_img, d.a_img_k, d.nseg = ai.data_ptr(), k, 0
+  if img_out:
+    oi = torch.zeros(lib.gcb_a_image_bytes(rows, n), dtype=torch.uint8, device=dev)
+    d.out_img, d.out, = oi.data_ptr(), None
   if pre:
     ptab = [torch.randn(40962, 512, device=dev) for _ in range(pre)]
     pidx = [torch.sort(torch.randint(0, 40962, (rows,), dtype=torch.int32, device=dev))[0] if i else
@@ -45,7 +51,7 @@ def run(rows, k, n, ln, act, csize, out_y=False, residual=False, idx=False, pre=
   lib.gcb_debug_trace(None)
   t = tr.cpu().numpy().reshape(64, 8)
   ntile = min(64, (rows + 127) // 128 // 148)
-  print(f"rows={rows} k={k} n={n} ln={ln} act={act} cluster={csize} out_y={out_y} res={residual} idx={idx} pre={pre}: {e0.elapsed_time(e1):.3f} ms; tiles/CTA~{ntile}")
+  print(f"rows={rows} k={k} n={n} ln={ln} act={act} cluster={csize} out_y={out_y} res={residual} idx={idx} pre={pre} img_in={img_in} img_out={img_out}: {e0.elapsed_time(e1):.3f} ms; tiles/CTA~{ntile}")
   base = t[1, 0]
   for i in range(1, min(ntile, 6)):
     r = t[i]
@@ -55,8 +61,9 @@ def run(rows, k, n, ln, act, csize, out_y=False, residual=False, idx=False, pre=
 
 rows = 148 * 128 * 8
 for cs in (2,):
-  run(rows, 512, 512, False, True, cs)
-  run(rows, 512, 512, False, True, cs, pre=2)
-  run(rows, 512, 512, False, False, cs)
-  run(rows, 512, 512, True, False, cs, out_y=True, residual=True)
-  run(rows, 1536, 512, False, True, cs, idx=True)
+  run(rows, 512, 512, False, True, cs, img_out=True)
+  run(rows, 512, 512, False, True, cs, img_in=True, img_out=True)
+  run(rows, 512, 512, False, True, cs, pre=2, img_in=True, img_out=True)
+  run(rows, 512, 512, True, False, cs, img_in=True)
+  run(rows, 512, 512, True, False, cs, out_y=True, residual=True, img_in=True)
+  run(rows, 1536, 512, False, True, cs, idx=True, img_out=True)
