@@ -296,7 +296,8 @@ def run_b200(args):
       for i in range(lo, min(lo + per_step_launches, n_launch)):
         f.write(f"{i - lo},{kinds[i]},{ms[i]:.4f},{flops[i] / 1e9:.2f},{nbytes[i] / 1e9:.4f}\n")
   # per-kind aggregation (this rank)
-  kind_names = {0: "mlp_layer_tc", 1: "segment_sum", 2: "pack", 3: "unpack", 4: "mlp_layer_simt"}
+  kind_names = {0: "mlp_layer_tc", 1: "segment_sum", 2: "pack", 3: "unpack", 4: "mlp_layer_simt",
+                5: "rows_to_image"}
   agg = {}
   for i in range(n_launch):
     a = agg.setdefault(kind_names[kinds[i]], [0.0, 0.0, 0.0, 0])

@@ -24,7 +24,7 @@ _fp = C.c_void_p   # device pointers are passed as raw addresses
 
 class Segment(C.Structure):
   _fields_ = [("table", _fp), ("idx", _fp), ("ld", C.c_int32), ("k", C.c_int32),
-              ("k_valid", C.c_int32), ("fan", C.c_int32)]
+              ("k_valid", C.c_int32), ("fan", C.c_int32), ("img", _fp)]
 
 
 class PreAdd(C.Structure):
@@ -40,7 +40,7 @@ class LayerDesc(C.Structure):
               ("out", _fp), ("ld_out", C.c_int32),
               ("out_y", _fp), ("ld_out_y", C.c_int32),
               ("precision", C.c_int32), ("n_pre_add", C.c_int32), ("pre_add", PreAdd * 2),
-              ("a_img", _fp), ("a_img_k", C.c_int32), ("out_img", _fp)]
+              ("out_img", _fp)]
 
 
 class MlpSplit(C.Structure):
@@ -74,8 +74,10 @@ class Model(C.Structure):
       ("proc_e_g2m_split", MlpSplit), ("proc_e_m2g_split", MlpSplit),
       ("proc_e_mesh_split", MlpSplit * GCB_MAX_MSG_STEPS),
       ("zero_bias", _fp), ("proj_grid", _fp), ("proj_mesh_a", _fp), ("proj_mesh_b", _fp),
-      ("hidden", _fp), ("edge_a", _fp), ("edge_b", _fp), ("grid_lat", _fp),
-      ("mesh_lat", _fp), ("mesh_agg", _fp), ("mesh_edge", _fp), ("mesh_msg", _fp),
+      ("hidden", _fp), ("edge_a_img", _fp), ("edge_b", _fp), ("grid_in_img", _fp),
+      ("mesh_in_img", _fp), ("grid_lat", _fp), ("grid_lat_img", _fp), ("mesh_lat", _fp),
+      ("mesh_lat_img", _fp), ("mesh_agg", _fp), ("mesh_agg_img", _fp), ("mesh_edge", _fp),
+      ("mesh_edge_img", _fp), ("mesh_msg", _fp), ("grid_agg_img", _fp),
   ]
 
 
@@ -86,6 +88,7 @@ EXPORTS = {
     "gcb_sm_count": (C.c_int, [C.c_int]),
     "gcb_packed_weight_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "gcb_a_image_bytes": (C.c_int64, [C.c_int64, C.c_int32]),
+    "gcb_rows_to_image": (C.c_int, [_fp, C.c_int32, C.c_int32, C.c_int64, C.c_int32, _fp, _fp]),
     "gcb_pack_weight_host": (C.c_int, [_fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _fp]),
     "gcb_layer_forward": (C.c_int, [C.POINTER(LayerDesc), _fp]),
     "gcb_segment_sum": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, _fp, C.c_int32, C.c_int32, _fp]),

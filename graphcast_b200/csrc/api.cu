@@ -107,26 +107,24 @@ int validate_layer(const gcb_layer_desc* d) {
   GCB_CHECK_ARG(d->rows >= 0, "rows < 0");
   GCB_CHECK_ARG(d->n == 256 || d->n == 512, "n must be 256 or 512");
   GCB_CHECK_ARG(d->n_valid > 0 && d->n_valid <= d->n, "n_valid out of range");
-  if (d->a_img != nullptr) {
-    GCB_CHECK_ARG(aligned16(d->a_img), "a_img unaligned");
-    GCB_CHECK_ARG(d->a_img_k > 0 && d->a_img_k % 16 == 0 && d->a_img_k / 16 <= gcb::kMaxKSteps,
-                  "a_img_k must be a positive multiple of 16");
-  } else {
-    GCB_CHECK_ARG(d->nseg >= 1 && d->nseg <= 3, "nseg must be 1..3");
-  }
+  GCB_CHECK_ARG(d->nseg >= 1 && d->nseg <= 3, "nseg must be 1..3");
   if (d->out_img != nullptr)
     GCB_CHECK_ARG(aligned16(d->out_img) && d->n == 512 && d->n_valid == 512,
                   "out_img requires n = n_valid = 512");
   int ksteps = 0;
-  for (int s = 0; s < d->nseg && d->a_img == nullptr; ++s) {
+  for (int s = 0; s < d->nseg; ++s) {
     const gcb_segment& g = d->seg[s];
-    GCB_CHECK_ARG(g.table != nullptr && aligned16(g.table), "segment table null/unaligned");
     GCB_CHECK_ARG(g.k > 0 && g.k % 16 == 0, "segment k must be a positive multiple of 16");
+    ksteps += g.k / 16;
+    if (g.img != nullptr) {
+      GCB_CHECK_ARG(aligned16(g.img), "segment image unaligned");
+      continue;
+    }
+    GCB_CHECK_ARG(g.table != nullptr && aligned16(g.table), "segment table null/unaligned");
     GCB_CHECK_ARG(g.k_valid > 0 && g.k_valid <= g.k && g.k_valid % 4 == 0,
                   "segment k_valid must be a multiple of 4 and <= k");
     GCB_CHECK_ARG(g.ld % 4 == 0 && g.ld >= g.k_valid, "segment ld must be a multiple of 4 and >= k_valid");
     GCB_CHECK_ARG(g.fan >= 1, "segment fan must be >= 1");
-    ksteps += g.k / 16;
   }
   GCB_CHECK_ARG(ksteps <= gcb::kMaxKSteps, "K too large");
   GCB_CHECK_ARG(d->bias != nullptr, "bias is null");
@@ -232,15 +230,31 @@ struct StepCtx {
 
 gcb_segment seg(const float* table, const int32_t* idx, int ld, int k, int k_valid, int fan = 1) {
   gcb_segment s;
+  memset(&s, 0, sizeof(s));
   s.table = table; s.idx = idx; s.ld = ld; s.k = k; s.k_valid = k_valid; s.fan = fan;
   return s;
 }
 
-// Two-layer MLP: hidden = swish(concat(segs) @ W0 + b0);  y = [LN](hidden @ W1 + b1).
+gcb_segment seg_img(const void* img, int k) {
+  gcb_segment s;
+  memset(&s, 0, sizeof(s));
+  s.img = img; s.k = k; s.k_valid = k; s.fan = 1;
+  return s;
+}
+
+struct MlpOut {
+  const float* residual = nullptr;   // fp32 [rows,512], added to the result
+  float* out = nullptr;              // residual + y (fp32)
+  int ld_out = 512;
+  float* out_y = nullptr;            // y alone (fp32)
+  void* out_img = nullptr;           // residual + y as an operand image
+};
+
+// Two-layer MLP: hidden = swish(concat(segs) @ W0 + b0 [+ gathered addends]) as an operand
+// image;  y = [LN](hidden @ W1 + b1), delivered as MlpOut says.
 int run_mlp(StepCtx& c, const gcb_mlp& w, int rows, int nseg, const gcb_segment* segs,
-            const float* residual, float* out, int ld_out, float* out_y,
-            const void* w0_packed_override = nullptr, const float* w0_f32_override = nullptr,
-            int n_pre = 0, const gcb_pre_add* pre = nullptr) {
+            const MlpOut& o, const void* w0_packed_override = nullptr,
+            const float* w0_f32_override = nullptr, int n_pre = 0, const gcb_pre_add* pre = nullptr) {
   if (rows == 0) return GCB_OK;
   gcb_layer_desc l0;
   memset(&l0, 0, sizeof(l0));
@@ -261,14 +275,15 @@ int run_mlp(StepCtx& c, const gcb_mlp& w, int rows, int nseg, const gcb_segment*
   if (rc) return rc;
   gcb_layer_desc l1;
   memset(&l1, 0, sizeof(l1));
-  l1.rows = rows; l1.n = w.n1; l1.n_valid = w.n1_valid; l1.nseg = 0;
-  l1.a_img = c.m->hidden; l1.a_img_k = 512;
+  l1.rows = rows; l1.n = w.n1; l1.n_valid = w.n1_valid; l1.nseg = 1;
+  l1.seg[0] = seg_img(c.m->hidden, 512);
   l1.w_packed = w.w1_packed; l1.w_f32 = w.w1_f32; l1.bias = w.b1;
   l1.ln_scale = w.ln_scale; l1.ln_offset = w.ln_offset;
   l1.act = GCB_ACT_NONE;
-  l1.residual = residual; l1.ld_res = 512;
-  l1.out = out; l1.ld_out = ld_out;
-  l1.out_y = out_y; l1.ld_out_y = 512;
+  l1.residual = o.residual; l1.ld_res = 512;
+  l1.out = o.out; l1.ld_out = o.ld_out;
+  l1.out_y = o.out_y; l1.ld_out_y = 512;
+  l1.out_img = o.out_img;
   l1.precision = c.m->precision;
   rc = gcb_layer_forward(&l1, c.stream);
   if (rc) return rc;
@@ -276,14 +291,14 @@ int run_mlp(StepCtx& c, const gcb_mlp& w, int rows, int nseg, const gcb_segment*
   return GCB_OK;
 }
 
-// Node-level projection P = v @ W  (no bias, no activation): one [rows,512]x[512,512] layer.
-int run_projection(StepCtx& c, const void* w_packed, const float* w_f32, const float* v, int rows,
-                   float* out) {
+// Node-level projection P = v @ W (no bias, no activation), v given as an operand image.
+int run_projection(StepCtx& c, const void* w_packed, const float* w_f32, const void* v_img,
+                   int rows, float* out) {
   if (rows == 0) return GCB_OK;
   gcb_layer_desc l;
   memset(&l, 0, sizeof(l));
   l.rows = rows; l.n = 512; l.n_valid = 512; l.nseg = 1;
-  l.seg[0] = seg(v, nullptr, 512, 512, 512);
+  l.seg[0] = seg_img(v_img, 512);
   l.w_packed = w_packed; l.w_f32 = w_f32; l.bias = c.m->zero_bias;
   l.act = GCB_ACT_NONE;
   l.out = out; l.ld_out = 512;
@@ -294,29 +309,36 @@ int run_projection(StepCtx& c, const void* w_packed, const float* w_f32, const f
   return GCB_OK;
 }
 
-// Edge MLP  LN.MLP([e | vs[snd] | vr[rcv]]).  With pregather the first layer is evaluated
-// as e @ W_e + (vs @ W_s)[snd] + (vr @ W_r)[rcv]: two node-level projections, then an edge
-// layer with K = 512 whose epilogue adds the gathered projections before the activation.
+// Edge MLP  LN.MLP([e | vs[snd] | vr[rcv]]).  With pregather the first layer is evaluated as
+// e @ W_e + (vs @ W_s)[snd] + (vr @ W_r)[rcv]: two node-level projections, then an edge layer
+// with K = 512 whose epilogue adds the gathered projections before the activation.
 int run_edge_mlp(StepCtx& c, const gcb_mlp& w, const gcb_mlp_split* split, int rows,
-                 const float* e, const float* vs, int n_s, const int32_t* snd, float* proj_s,
-                 const float* vr, int n_r, const int32_t* rcv, float* proj_r,
-                 const float* residual, float* out, float* out_y) {
+                 const void* e_img,
+                 const float* vs, const void* vs_img, int n_s, const int32_t* snd, float* proj_s,
+                 const float* vr, const void* vr_img, int n_r, const int32_t* rcv, float* proj_r,
+                 const MlpOut& o) {
   const int D = 512;
   gcb_segment s[3];
-  if (!c.m->pregather || split == nullptr) {
-    s[0] = seg(e, nullptr, D, D, D);
+  s[0] = seg_img(e_img, D);
+  if (!c.m->pregather) {
     s[1] = seg(vs, snd, D, D, D);
     s[2] = seg(vr, rcv, D, D, D);
-    return run_mlp(c, w, rows, 3, s, residual, out, D, out_y);
+    return run_mlp(c, w, rows, 3, s, o);
   }
   int rc;
-  if ((rc = run_projection(c, split->ws_packed, split->ws_f32, vs, n_s, proj_s))) return rc;
-  if ((rc = run_projection(c, split->wr_packed, split->wr_f32, vr, n_r, proj_r))) return rc;
+  if ((rc = run_projection(c, split->ws_packed, split->ws_f32, vs_img, n_s, proj_s))) return rc;
+  if ((rc = run_projection(c, split->wr_packed, split->wr_f32, vr_img, n_r, proj_r))) return rc;
   gcb_pre_add pre[2];
   pre[0].table = proj_s; pre[0].idx = snd; pre[0].ld = D; pre[0].pad_ = 0;
   pre[1].table = proj_r; pre[1].idx = rcv; pre[1].ld = D; pre[1].pad_ = 0;
-  s[0] = seg(e, nullptr, D, D, D);
-  return run_mlp(c, w, rows, 1, s, residual, out, D, out_y, split->we_packed, split->we_f32, 2, pre);
+  return run_mlp(c, w, rows, 1, s, o, split->we_packed, split->we_f32, 2, pre);
+}
+
+int to_image(StepCtx& c, const float* src, int ld, int fan, long long rows, int k, void* img) {
+  int rc = gcb_rows_to_image(src, ld, fan, rows, k, img, c.stream);
+  if (rc) return rc;
+  c.launches += 1;
+  return GCB_OK;
 }
 
 }  // namespace
@@ -375,11 +397,11 @@ int gcb_layer_forward(const gcb_layer_desc* d, void* stream) {
   if (d->rows == 0) return GCB_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double kv = 0, a_elems = 0;
-  for (int i = 0; i < d->nseg && d->a_img == nullptr; ++i) {
-    kv += d->seg[i].k_valid;
-    a_elems += static_cast<double>(d->seg[i].k_valid) * d->seg[i].fan;
+  for (int i = 0; i < d->nseg; ++i) {
+    const double w = d->seg[i].img ? d->seg[i].k : d->seg[i].k_valid;
+    kv += w;
+    a_elems += w * (d->seg[i].img ? 1 : d->seg[i].fan);
   }
-  if (d->a_img != nullptr) { kv = d->a_img_k; a_elems = d->a_img_k; }
   const double rows = d->rows;
   a_elems += static_cast<double>(d->n_pre_add) * d->n_valid;
   const double flops = 2.0 * rows * kv * d->n_valid;
@@ -445,11 +467,39 @@ int gcb_unpack_grid_outputs(const float* y, int32_t ld_y, int32_t n_out, int64_t
   return GCB_OK;
 }
 
+int gcb_rows_to_image(const float* src, int32_t ld, int32_t fan, int64_t rows, int32_t k,
+                      void* img, void* stream) {
+  GCB_CHECK_ARG(src && img && aligned16(src) && aligned16(img), "null/unaligned pointer");
+  GCB_CHECK_ARG(k > 0 && k % 16 == 0 && ld % 4 == 0 && ld >= k && fan >= 1, "bad k / ld / fan");
+  if (rows == 0) return GCB_OK;
+  const size_t smem = 32 * static_cast<size_t>(k + 4) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GCB_CUDA(cudaFuncSetAttribute(gcb::rows_to_image_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  GCB_CHECK_ARG(smem <= 96 * 1024, "k too large");
+  const long long padded = (rows + 127) / 128 * 128;      // zero-fill the tail of the last tile
+  const unsigned grid = static_cast<unsigned>((padded + 31) / 32);
+  ProfScope prof(static_cast<cudaStream_t>(stream), GCB_KIND_ROWS_TO_IMAGE, 0.0,
+                 4.0 * rows * k * (fan + 1.0));
+  gcb::rows_to_image_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      src, ld, fan, rows, k, static_cast<unsigned char*>(img));
+  GCB_CUDA(cudaGetLastError());
+  return GCB_OK;
+}
+
 int gcb_forward(const gcb_model* m, const float* grid_in, float* grid_out, void* stream,
                 int32_t* launches) {
   GCB_CHECK_ARG(m && grid_in && grid_out, "null pointer");
   GCB_CHECK_ARG(m->msg_steps >= 1 && m->msg_steps <= GCB_MAX_MSG_STEPS, "msg_steps out of range");
   GCB_CHECK_ARG(m->e_m2g == 3 * m->num_grid, "mesh2grid must have fan-in 3");
+  GCB_CHECK_ARG(m->hidden && m->edge_a_img && m->edge_b && m->grid_in_img && m->mesh_in_img &&
+                    m->grid_lat && m->grid_lat_img && m->mesh_lat && m->mesh_lat_img &&
+                    m->mesh_agg && m->mesh_agg_img && m->mesh_edge && m->mesh_edge_img &&
+                    m->mesh_msg && m->grid_agg_img,
+                "workspace pointer is null");
   if (m->pregather)
     GCB_CHECK_ARG(m->zero_bias && m->proj_grid && m->proj_mesh_a && m->proj_mesh_b,
                   "pregather needs zero_bias and the proj_* buffers");
@@ -457,68 +507,87 @@ int gcb_forward(const gcb_model* m, const float* grid_in, float* grid_out, void*
   int rc;
   gcb_segment s[3];
   const int D = 512;
+  MlpOut o;
 
   // ---------------- encoder: grid2mesh_gnn (graphcast.py:550-604) ----------------
-  // vg0 = LN.MLP(grid_in)  -> grid_lat
-  s[0] = seg(grid_in, nullptr, m->c_in_pad, m->c_in_pad, m->c_in_valid);
-  if ((rc = run_mlp(c, m->enc_grid, m->num_grid, 1, s, nullptr, m->grid_lat, D, nullptr))) return rc;
-  // vm0 = LN.MLP(mesh_in)  -> mesh_lat
-  s[0] = seg(m->mesh_in, nullptr, m->c_in_pad, m->c_in_pad, m->c_in_valid);
-  if ((rc = run_mlp(c, m->enc_mesh, m->num_mesh, 1, s, nullptr, m->mesh_lat, D, nullptr))) return rc;
-  // e1 = LN.MLP(g2m edge feats)  -> edge_a
+  // vg0 = LN.MLP(grid_in)  -> grid_lat (+ image)
+  if ((rc = to_image(c, grid_in, m->c_in_pad, 1, m->num_grid, m->c_in_pad, m->grid_in_img))) return rc;
+  s[0] = seg_img(m->grid_in_img, m->c_in_pad);
+  o = MlpOut(); o.out = m->grid_lat; o.out_img = m->grid_lat_img;
+  if ((rc = run_mlp(c, m->enc_grid, m->num_grid, 1, s, o))) return rc;
+  // vm0 = LN.MLP(mesh_in)  -> mesh_lat (+ image)
+  s[0] = seg_img(m->mesh_in_img, m->c_in_pad);
+  o = MlpOut(); o.out = m->mesh_lat; o.out_img = m->mesh_lat_img;
+  if ((rc = run_mlp(c, m->enc_mesh, m->num_mesh, 1, s, o))) return rc;
+  // e1 = LN.MLP(g2m edge feats)  -> image only (its fp32 form is never needed)
   s[0] = seg(m->g2m_feat, nullptr, 4, 16, 4);
-  if ((rc = run_mlp(c, m->enc_e_g2m, m->e_g2m, 1, s, nullptr, m->edge_a, D, nullptr))) return rc;
+  o = MlpOut(); o.out_img = m->edge_a_img;
+  if ((rc = run_mlp(c, m->enc_e_g2m, m->e_g2m, 1, s, o))) return rc;
   // m1 = LN.MLP([e1 | vg0[snd] | vm0[rcv]])  -> edge_b   (edge residual e1+m1 is dead)
-  if ((rc = run_edge_mlp(c, m->proc_e_g2m, &m->proc_e_g2m_split, m->e_g2m, m->edge_a,
-                         m->grid_lat, m->num_grid, m->g2m_snd, m->proj_grid,
-                         m->mesh_lat, m->num_mesh, m->g2m_rcv, m->proj_mesh_a,
-                         nullptr, m->edge_b, nullptr))) return rc;
+  o = MlpOut(); o.out = m->edge_b;
+  if ((rc = run_edge_mlp(c, m->proc_e_g2m, &m->proc_e_g2m_split, m->e_g2m, m->edge_a_img,
+                         m->grid_lat, m->grid_lat_img, m->num_grid, m->g2m_snd, m->proj_grid,
+                         m->mesh_lat, m->mesh_lat_img, m->num_mesh, m->g2m_rcv, m->proj_mesh_a, o)))
+    return rc;
   // agg1 = segment_sum(m1)
   if ((rc = gcb_segment_sum(m->edge_b, D, m->g2m_row_ptr, m->num_mesh, m->mesh_agg, D, D, stream))) return rc;
   c.launches += 1;
+  if ((rc = to_image(c, m->mesh_agg, D, 1, m->num_mesh, D, m->mesh_agg_img))) return rc;
   // vm1 = vm0 + LN.MLP([vm0 | agg1])  (in place)
-  s[0] = seg(m->mesh_lat, nullptr, D, D, D);
-  s[1] = seg(m->mesh_agg, nullptr, D, D, D);
-  if ((rc = run_mlp(c, m->proc_n_mesh_g2m, m->num_mesh, 2, s, m->mesh_lat, m->mesh_lat, D, nullptr))) return rc;
+  s[0] = seg_img(m->mesh_lat_img, D);
+  s[1] = seg_img(m->mesh_agg_img, D);
+  o = MlpOut(); o.residual = m->mesh_lat; o.out = m->mesh_lat; o.out_img = m->mesh_lat_img;
+  if ((rc = run_mlp(c, m->proc_n_mesh_g2m, m->num_mesh, 2, s, o))) return rc;
   // vg1 = vg0 + LN.MLP([vg0])  (in place; grid nodes receive nothing in grid2mesh)
-  s[0] = seg(m->grid_lat, nullptr, D, D, D);
-  if ((rc = run_mlp(c, m->proc_n_grid_g2m, m->num_grid, 1, s, m->grid_lat, m->grid_lat, D, nullptr))) return rc;
+  s[0] = seg_img(m->grid_lat_img, D);
+  o = MlpOut(); o.residual = m->grid_lat; o.out = m->grid_lat; o.out_img = m->grid_lat_img;
+  if ((rc = run_mlp(c, m->proc_n_grid_g2m, m->num_grid, 1, s, o))) return rc;
 
   // ---------------- processor: mesh_gnn (graphcast.py:606-639) --------------------
   s[0] = seg(m->mesh_feat, nullptr, 4, 16, 4);
-  if ((rc = run_mlp(c, m->enc_e_mesh, m->e_mesh, 1, s, nullptr, m->mesh_edge, D, nullptr))) return rc;
+  o = MlpOut(); o.out = m->mesh_edge; o.out_img = m->mesh_edge_img;
+  if ((rc = run_mlp(c, m->enc_e_mesh, m->e_mesh, 1, s, o))) return rc;
   for (int k = 0; k < m->msg_steps; ++k) {
     const bool last = (k == m->msg_steps - 1);
-    // m = LN.MLP([e | v[snd] | v[rcv]]) -> mesh_msg;  e += m (skipped on the last
-    // step: the updated edge latents are never read again).
-    if ((rc = run_edge_mlp(c, m->proc_e_mesh[k], &m->proc_e_mesh_split[k], m->e_mesh, m->mesh_edge,
-                           m->mesh_lat, m->num_mesh, m->mesh_snd, m->proj_mesh_a,
-                           m->mesh_lat, m->num_mesh, m->mesh_rcv, m->proj_mesh_b,
-                           last ? nullptr : m->mesh_edge, last ? nullptr : m->mesh_edge,
-                           m->mesh_msg))) return rc;
+    // m = LN.MLP([e | v[snd] | v[rcv]]) -> mesh_msg;  e += m (skipped on the last step: the
+    // updated edge latents are never read again).
+    o = MlpOut(); o.out_y = m->mesh_msg;
+    if (!last) { o.residual = m->mesh_edge; o.out = m->mesh_edge; o.out_img = m->mesh_edge_img; }
+    if ((rc = run_edge_mlp(c, m->proc_e_mesh[k], &m->proc_e_mesh_split[k], m->e_mesh, m->mesh_edge_img,
+                           m->mesh_lat, m->mesh_lat_img, m->num_mesh, m->mesh_snd, m->proj_mesh_a,
+                           m->mesh_lat, m->mesh_lat_img, m->num_mesh, m->mesh_rcv, m->proj_mesh_b, o)))
+      return rc;
     if ((rc = gcb_segment_sum(m->mesh_msg, D, m->mesh_row_ptr, m->num_mesh, m->mesh_agg, D, D, stream))) return rc;
     c.launches += 1;
+    if ((rc = to_image(c, m->mesh_agg, D, 1, m->num_mesh, D, m->mesh_agg_img))) return rc;
     // v += LN.MLP([v | agg])
-    s[0] = seg(m->mesh_lat, nullptr, D, D, D);
-    s[1] = seg(m->mesh_agg, nullptr, D, D, D);
-    if ((rc = run_mlp(c, m->proc_n_mesh[k], m->num_mesh, 2, s, m->mesh_lat, m->mesh_lat, D, nullptr))) return rc;
+    s[0] = seg_img(m->mesh_lat_img, D);
+    s[1] = seg_img(m->mesh_agg_img, D);
+    o = MlpOut(); o.residual = m->mesh_lat; o.out = m->mesh_lat; o.out_img = m->mesh_lat_img;
+    if ((rc = run_mlp(c, m->proc_n_mesh[k], m->num_mesh, 2, s, o))) return rc;
   }
 
   // ---------------- decoder: mesh2grid_gnn (graphcast.py:641-678) ------------------
   s[0] = seg(m->m2g_feat, nullptr, 4, 16, 4);
-  if ((rc = run_mlp(c, m->enc_e_m2g, m->e_m2g, 1, s, nullptr, m->edge_a, D, nullptr))) return rc;
+  o = MlpOut(); o.out_img = m->edge_a_img;
+  if ((rc = run_mlp(c, m->enc_e_m2g, m->e_m2g, 1, s, o))) return rc;
   // m3 = LN.MLP([e3 | v[snd] | vg1[rcv]]) -> edge_b
-  if ((rc = run_edge_mlp(c, m->proc_e_m2g, &m->proc_e_m2g_split, m->e_m2g, m->edge_a,
-                         m->mesh_lat, m->num_mesh, m->m2g_snd, m->proj_mesh_a,
-                         m->grid_lat, m->num_grid, m->m2g_rcv, m->proj_grid,
-                         nullptr, m->edge_b, nullptr))) return rc;
-  // vg2 = vg1 + LN.MLP([vg1 | sum of the 3 incoming messages])  (in place)
-  s[0] = seg(m->grid_lat, nullptr, D, D, D);
-  s[1] = seg(m->edge_b, nullptr, D, D, D, /*fan=*/3);
-  if ((rc = run_mlp(c, m->proc_n_grid_m2g, m->num_grid, 2, s, m->grid_lat, m->grid_lat, D, nullptr))) return rc;
+  o = MlpOut(); o.out = m->edge_b;
+  if ((rc = run_edge_mlp(c, m->proc_e_m2g, &m->proc_e_m2g_split, m->e_m2g, m->edge_a_img,
+                         m->mesh_lat, m->mesh_lat_img, m->num_mesh, m->m2g_snd, m->proj_mesh_a,
+                         m->grid_lat, m->grid_lat_img, m->num_grid, m->m2g_rcv, m->proj_grid, o)))
+    return rc;
+  // sum of the 3 incoming messages of every grid node, as an operand image
+  if ((rc = to_image(c, m->edge_b, D, 3, m->num_grid, D, m->grid_agg_img))) return rc;
+  // vg2 = vg1 + LN.MLP([vg1 | agg3])  (in place)
+  s[0] = seg_img(m->grid_lat_img, D);
+  s[1] = seg_img(m->grid_agg_img, D);
+  o = MlpOut(); o.residual = m->grid_lat; o.out = m->grid_lat; o.out_img = m->grid_lat_img;
+  if ((rc = run_mlp(c, m->proc_n_grid_m2g, m->num_grid, 2, s, o))) return rc;
   // out = MLP(vg2), no LayerNorm (deep_typed_graph_net.py:314-322)
-  s[0] = seg(m->grid_lat, nullptr, D, D, D);
-  if ((rc = run_mlp(c, m->dec_grid, m->num_grid, 1, s, nullptr, grid_out, 256, nullptr))) return rc;
+  s[0] = seg_img(m->grid_lat_img, D);
+  o = MlpOut(); o.out = grid_out; o.ld_out = 256;
+  if ((rc = run_mlp(c, m->dec_grid, m->num_grid, 1, s, o))) return rc;
 
   if (launches) *launches = c.launches;
   return GCB_OK;

@@ -1,6 +1,7 @@
 // HBM-bound helper kernels of the GraphCast step: receiver-sorted segment sum and
 // the channel pack / unpack transposes (with the normalisation affine fused in).
 #pragma once
+#include <cuda_bf16.h>
 #include <stdint.h>
 
 namespace gcb {
@@ -115,6 +116,61 @@ unpack_grid_outputs_kernel(const float* __restrict__ y, int ld_y, int n_out, lon
         if (ap >= 0) v += add_planes[static_cast<long long>(ap) * n_nodes + node];
       }
       planes_out[static_cast<long long>(c) * n_nodes + node] = v;
+    }
+  }
+}
+
+// img[r, 0:k] = sum_{j<fan} src[r*fan + j, 0:k] written as an operand image (bf16 hi/lo
+// in the tensor-core A layout, see gcb_layer_desc).  A block handles 32 output rows:
+// phase 1 sums the fan input rows with coalesced float4 reads into a padded shared tile,
+// phase 2 lets lane = row emit the 16-byte image pieces, so a warp stores 512 contiguous
+// bytes.  HBM-bound: fan*k*4 bytes read + ~k*4 written per row.
+__global__ void __launch_bounds__(256)
+rows_to_image_kernel(const float* __restrict__ src, int ld, int fan, long long rows, int k,
+                     unsigned char* __restrict__ img) {
+  extern __shared__ float tile[];                 // [32][k + 4]
+  const int kp = k + 4;
+  const long long row0 = static_cast<long long>(blockIdx.x) * 32;
+  const int nvec = k >> 2;                        // float4 per row
+  for (int e = threadIdx.x; e < 32 * nvec; e += blockDim.x) {
+    const int r = e / nvec, c4 = e % nvec;
+    const long long grow = row0 + r;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (grow < rows) {
+      const float* p = src + grow * fan * ld + c4 * 4;
+      for (int j = 0; j < fan; ++j) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p + static_cast<long long>(j) * ld));
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
+    }
+    *reinterpret_cast<float4*>(tile + r * kp + c4 * 4) = acc;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long grow = row0 + lane;
+  const long long t = grow >> 7;
+  const int r = static_cast<int>(grow & 127);
+  const int ksteps = k >> 4;
+  // 16-byte pieces: (K-step, chunk) pairs distributed over the 8 warps
+  for (int piece = warp; piece < ksteps * 2; piece += 8) {
+    const int ks = piece >> 1, c = piece & 1;
+    const float* x = tile + lane * kp + ks * 16 + c * 8;
+    const float4 a = *reinterpret_cast<const float4*>(x), b = *reinterpret_cast<const float4*>(x + 4);
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    const float2 f2 = __bfloat1622float2(h2), f3 = __bfloat1622float2(h3);
+    __nv_bfloat162 l0 = __floats2bfloat162_rn(a.x - f0.x, a.y - f0.y), l1 = __floats2bfloat162_rn(a.z - f1.x, a.w - f1.y);
+    __nv_bfloat162 l2 = __floats2bfloat162_rn(b.x - f2.x, b.y - f2.y), l3 = __floats2bfloat162_rn(b.z - f3.x, b.w - f3.y);
+    if (grow < ((rows + 127) >> 7 << 7)) {        // rows of the last tile beyond `rows` get zeros
+      unsigned char* dst = img + (static_cast<size_t>(t) * ksteps + ks) * 8448 + c * 2112 + r * 16;
+      uint4 hv, lv;
+      hv.x = *reinterpret_cast<unsigned int*>(&h0); hv.y = *reinterpret_cast<unsigned int*>(&h1);
+      hv.z = *reinterpret_cast<unsigned int*>(&h2); hv.w = *reinterpret_cast<unsigned int*>(&h3);
+      lv.x = *reinterpret_cast<unsigned int*>(&l0); lv.y = *reinterpret_cast<unsigned int*>(&l1);
+      lv.z = *reinterpret_cast<unsigned int*>(&l2); lv.w = *reinterpret_cast<unsigned int*>(&l3);
+      *reinterpret_cast<uint4*>(dst) = hv;
+      *reinterpret_cast<uint4*>(dst + 4224) = lv;
     }
   }
 }

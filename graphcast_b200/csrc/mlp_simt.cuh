@@ -47,10 +47,9 @@ mlp_layer_simt_kernel(const __grid_constant__ gcb_layer_desc d) {
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
   int kglobal = 0;
-  const int nseg_eff = d.a_img ? 1 : d.nseg;
-  for (int s = 0; s < nseg_eff; ++s) {
+  for (int s = 0; s < d.nseg; ++s) {
     gcb_segment sg = d.seg[s];
-    if (d.a_img) { sg.k = d.a_img_k; sg.k_valid = d.a_img_k; sg.fan = 1; sg.idx = nullptr; }
+    if (sg.img) { sg.k_valid = sg.k; sg.fan = 1; sg.idx = nullptr; }
     for (int k0 = 0; k0 < sg.k; k0 += kSimtK, kglobal += kSimtK) {
       // A tile: 32 rows x 16 -> 512 elements, 2 per thread.
       for (int e = tid; e < kSimtRows * kSimtK; e += kSimtThreads) {
@@ -58,9 +57,9 @@ mlp_layer_simt_kernel(const __grid_constant__ gcb_layer_desc d) {
         const long long grow = row0 + r;
         float v = 0.f;
         if (grow < d.rows && (k0 + kk) < sg.k_valid) {
-          if (d.a_img) {
-            const unsigned char* p = static_cast<const unsigned char*>(d.a_img) +
-                                     a_image_offset(grow, k0 + kk, d.a_img_k);
+          if (sg.img) {
+            const unsigned char* p = static_cast<const unsigned char*>(sg.img) +
+                                     a_image_offset(grow, k0 + kk, sg.k);
             v = bf16_bits_to_float(*reinterpret_cast<const unsigned short*>(p)) +
                 bf16_bits_to_float(*reinterpret_cast<const unsigned short*>(p + 4224));
           } else {
@@ -138,8 +137,9 @@ mlp_layer_simt_kernel(const __grid_constant__ gcb_layer_desc d) {
       if (d.ln_scale) x = (x - mean) * rstd * d.ln_scale[c] + d.ln_offset[c];
       if (d.out_img) {
         unsigned char* p = static_cast<unsigned char*>(d.out_img) + a_image_offset(grow, c, n);
-        const __nv_bfloat16 hi = __float2bfloat16_rn(x);
-        const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+        const float xo = x + (d.residual ? d.residual[grow * d.ld_res + c] : 0.f);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(xo);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(xo - __bfloat162float(hi));
         *reinterpret_cast<__nv_bfloat16*>(p) = hi;
         *reinterpret_cast<__nv_bfloat16*>(p + 4224) = lo;
       }

@@ -83,7 +83,8 @@ __device__ __forceinline__ void trace(uint32_t tile_iter, int ev) {
 
 struct KStepInfo {
   uint8_t seg;
-  uint16_t koff;  // element offset of this K-step inside its segment
+  uint8_t is_img;  // 1: this K-step's A block comes from the segment's operand image (TMA)
+  uint16_t koff;   // element offset of this K-step inside its segment
 };
 
 // Per-segment fields copied to shared memory once: reading them from the kernel
@@ -91,7 +92,8 @@ struct KStepInfo {
 struct SegInfo {
   const float* table;
   const int32_t* idx;
-  int ld, k_valid, fan, pad;
+  const uint8_t* img;
+  int ld, k_valid, fan, ksteps;
 };
 struct PreAddInfo {
   const float* table;
@@ -128,14 +130,13 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
   const int lane = threadIdx.x & 31;
   const int n = d.n;
   const int num_tiles = (d.rows + kTileM - 1) / kTileM;
-  // Operand-image input: A tiles arrive by TMA bulk copy instead of the gather warps.
-  const uint8_t* const a_img = static_cast<const uint8_t*>(d.a_img);
-  const bool a_is_img = a_img != nullptr;
+  // Segments backed by an operand image are streamed by TMA; if every segment is,
+  // the gather warps have no A work at all (a_is_img).
   int ksteps = 0;
-  if (a_is_img) {
-    ksteps = d.a_img_k / kKStep;
-  } else {
-    for (int s = 0; s < d.nseg; ++s) ksteps += d.seg[s].k / kKStep;
+  bool a_is_img = true;
+  for (int s = 0; s < d.nseg; ++s) {
+    ksteps += d.seg[s].k / kKStep;
+    a_is_img = a_is_img && (d.seg[s].img != nullptr);
   }
   uint8_t* const out_img = static_cast<uint8_t*>(d.out_img);
   constexpr bool has_ln = kLN;
@@ -166,18 +167,21 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
     for (int s = 0; s < d.nseg; ++s) {
       s_seg[s].table = d.seg[s].table;
       s_seg[s].idx = d.seg[s].idx;
+      s_seg[s].img = static_cast<const uint8_t*>(d.seg[s].img);
       s_seg[s].ld = d.seg[s].ld;
       s_seg[s].k_valid = d.seg[s].k_valid;
       s_seg[s].fan = d.seg[s].fan;
+      s_seg[s].ksteps = d.seg[s].k / kKStep;
     }
     for (int s = 0; s < n_pre; ++s) {
       s_pre[s].table = d.pre_add[s].table;
       s_pre[s].idx = d.pre_add[s].idx;
       s_pre[s].ld = d.pre_add[s].ld;
     }
-    for (int s = 0; s < d.nseg && !a_is_img; ++s)
+    for (int s = 0; s < d.nseg; ++s)
       for (int k = 0; k < d.seg[s].k; k += kKStep) {
         ks_info[ks].seg = static_cast<uint8_t>(s);
+        ks_info[ks].is_img = d.seg[s].img != nullptr ? 1 : 0;
         ks_info[ks].koff = static_cast<uint16_t>(k);
         ++ks;
       }
@@ -216,17 +220,21 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
       uint32_t it = 0;
       for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles); base += tile_stride) {
         const uint32_t tile = base + crank;
-        const bool a_copy = a_is_img && tile < static_cast<uint32_t>(num_tiles);
-        const uint8_t* a_src = a_img + static_cast<size_t>(tile) * ksteps * GCB_A_IMAGE_BLOCK;
+        const bool tile_ok = tile < static_cast<uint32_t>(num_tiles);   // else: dummy tile
         for (int ks = 0; ks < ksteps; ++ks, ++it) {
           const uint32_t stage = it % Cfg::kStages;
           const uint32_t phase = (it / Cfg::kStages) & 1;
+          const KStepInfo ki = ks_info[ks];
+          const bool a_copy = tile_ok && ki.is_img;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);     // free in every CTA of the cluster
           ptx::mbar_arrive_expect_tx(&full_bar[stage], b_bytes + (a_copy ? a_bytes : 0u));
-          if (a_copy)
+          if (a_copy) {
+            const SegInfo sg = s_seg[ki.seg];
             ptx::bulk_g2s(stage_base + stage * Cfg::kStageBytes,
-                          a_src + static_cast<size_t>(ks) * GCB_A_IMAGE_BLOCK, a_bytes,
-                          &full_bar[stage]);
+                          sg.img + (static_cast<size_t>(tile) * sg.ksteps + (ki.koff >> 4)) *
+                                       GCB_A_IMAGE_BLOCK,
+                          a_bytes, &full_bar[stage]);
+          }
           uint8_t* dst = stage_base + stage * Cfg::kStageBytes + Cfg::kAStageBytes;
           const uint8_t* src = wimg + ks * b_stride;
           if (csize == 1) {
@@ -397,25 +405,6 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += g[j];
         }
-        if (out_img != nullptr && (base + crank) < static_cast<uint32_t>(num_tiles)) {
-          // Operand image of this tile for the next layer: thread = row, so the 16-byte
-          // pieces of 32 consecutive rows are contiguous -> 512-byte coalesced warp stores.
-          uint8_t* blk = out_img + (static_cast<size_t>(base + crank) * (n >> 4) + (c0 >> 4)) * GCB_A_IMAGE_BLOCK +
-                         (ew * 32 + lane) * 16;
-#pragma unroll
-          for (int ks2 = 0; ks2 < 2; ++ks2) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              const float* x = &v[ks2 * 16 + c * 8];
-              uint2 h0, l0, h1, l1;
-              ptx::split_bf16x4(make_float4(x[0], x[1], x[2], x[3]), h0, l0);
-              ptx::split_bf16x4(make_float4(x[4], x[5], x[6], x[7]), h1, l1);
-              uint8_t* dst = blk + ks2 * GCB_A_IMAGE_BLOCK + c * kALbo;
-              *reinterpret_cast<uint4*>(dst) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-              *reinterpret_cast<uint4*>(dst + kAPartBytes) = make_uint4(l0.x, l0.y, l1.x, l1.y);
-            }
-          }
-        }
         if (out_ptr != nullptr || outy_ptr != nullptr) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
@@ -443,6 +432,12 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
               for (int i = 0; i < 8; ++i)
                 *reinterpret_cast<float4*>(out_ptr + (row0 + rsub + 4 * i) * ld_out + col) = y[i];
             }
+            if (out_img != nullptr && res_ptr != nullptr) {
+              // The image must hold residual + y: hand the sums back through the tile.
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(my_epi + (rsub + 4 * i) * kEpiRowFloats + cg * 4) = y[i];
+            }
           } else {
             // Ragged edge (last rows of the matrix / last partial column block).
             for (int i = 0; i < 8; ++i) {
@@ -451,15 +446,41 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
               if (grow < rows_total) {
                 for (int e = 0; e < 4 && col + e < n_valid; ++e) {
                   const float yv = my_epi[r * kEpiRowFloats + cg * 4 + e];
+                  const float ov = yv + (res_ptr ? res_ptr[grow * ld_res + col + e] : 0.f);
                   if (outy_ptr != nullptr) outy_ptr[grow * ld_outy + col + e] = yv;
-                  if (out_ptr != nullptr)
-                    out_ptr[grow * ld_out + col + e] =
-                        yv + (res_ptr ? res_ptr[grow * ld_res + col + e] : 0.f);
+                  if (out_ptr != nullptr) out_ptr[grow * ld_out + col + e] = ov;
+                  if (out_img != nullptr) my_epi[r * kEpiRowFloats + cg * 4 + e] = ov;
                 }
               }
             }
           }
     __syncwarp();
+          if (out_img != nullptr && res_ptr != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(&v[4 * q]) =
+                  *reinterpret_cast<const float4*>(my_epi + lane * kEpiRowFloats + q * 4);
+            __syncwarp();
+          }
+        }
+        if (out_img != nullptr && (base + crank) < static_cast<uint32_t>(num_tiles)) {
+          // Operand image of this tile for the next layer: thread = row, so the 16-byte
+          // pieces of 32 consecutive rows are contiguous -> 512-byte coalesced warp stores.
+          uint8_t* blk = out_img + (static_cast<size_t>(base + crank) * (n >> 4) + (c0 >> 4)) * GCB_A_IMAGE_BLOCK +
+                         (ew * 32 + lane) * 16;
+#pragma unroll
+          for (int ks2 = 0; ks2 < 2; ++ks2) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const float* x = &v[ks2 * 16 + c * 8];
+              uint2 h0, l0, h1, l1;
+              ptx::split_bf16x4(make_float4(x[0], x[1], x[2], x[3]), h0, l0);
+              ptx::split_bf16x4(make_float4(x[4], x[5], x[6], x[7]), h1, l1);
+              uint8_t* dst = blk + ks2 * GCB_A_IMAGE_BLOCK + c * kALbo;
+              *reinterpret_cast<uint4*>(dst) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+              *reinterpret_cast<uint4*>(dst + kAPartBytes) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+            }
+          }
         }
       }
       if (ew == 0 && lane == 0) trace(tile_iter, 5);
@@ -544,7 +565,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
         }
       }
       float4 cur[4];
-      bool have_cur = false;
+      bool have_cur = false, cur_img = false;
       uint32_t cur_it = 0;
       // Software pipeline over the K-steps this group owns: the loads of the next
       // owned K-step are in flight while the current one is converted and stored.
@@ -553,7 +574,8 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
         // Normal mode: the two groups alternate K-steps.  Gather mode: group 0 owns all.
         const bool mine = (ks < ksteps) && (gather_mode || (this_it & 1u) == static_cast<uint32_t>(group));
         float4 nxt[4];
-        if (mine) {
+        const bool img_step = mine && ks_info[ks].is_img;   // TMA brings the data: arrive only
+        if (mine && !img_step) {
           const int s = ks_info[ks].seg;
           const int koff = ks_info[ks].koff + sub * 4;
           const SegInfo sg = s_seg[s];
@@ -578,13 +600,15 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
           const uint32_t phase = (cur_it / Cfg::kStages) & 1;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_hi = stage_base + stage * Cfg::kStageBytes;
+          if (!cur_img) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint2 hi, lo;
-            ptx::split_bf16x4(cur[i], hi, lo);
-            const uint32_t off = sts_off + (rg + 32 * i) * 16;
-            *reinterpret_cast<uint2*>(a_hi + off) = hi;
-            if (kSplit) *reinterpret_cast<uint2*>(a_hi + kAPartBytes + off) = lo;
+            for (int i = 0; i < 4; ++i) {
+              uint2 hi, lo;
+              ptx::split_bf16x4(cur[i], hi, lo);
+              const uint32_t off = sts_off + (rg + 32 * i) * 16;
+              *reinterpret_cast<uint2*>(a_hi + off) = hi;
+              if (kSplit) *reinterpret_cast<uint2*>(a_hi + kAPartBytes + off) = lo;
+            }
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
@@ -595,6 +619,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
           cur_it = this_it;
+          cur_img = img_step;
           have_cur = true;
         }
       }

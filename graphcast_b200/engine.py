@@ -11,7 +11,10 @@ runs in libgraphcast_b200.so.  HBM layout (fp32 unless noted):
   mesh_edge  [E_mesh, 512]      latent multi-mesh edges (receiver-sorted order)
   mesh_msg   [E_mesh, 512]      messages of the current step
   edge_a/b   [max(E_g2m,E_m2g), 512]  bipartite edge latents / messages
-  hidden     [max rows, 512]    hidden activations between the two layers of an MLP
+  hidden     image [max rows, 512]  hidden activations between the two layers of an MLP
+  *_img      operand images (bf16 hi|lo in the tensor-core A layout) of every tensor that
+             is consumed as an identity-row A operand: grid_in, grid_lat, mesh_lat,
+             mesh_agg, mesh_edge, the embedded bipartite edges, the summed m2g messages
   grid_out   [Ng, 256]          decoder output (n_out valid columns)
   weights    per linear layer: bf16 hi|lo tile image (tcgen05 B operand) + fp32 copy
 """
@@ -226,31 +229,48 @@ class Engine:
       m.zero_bias = self._ptr(self._dev(np.zeros([D], np.float32), torch.float32))
 
   # -- workspace ---------------------------------------------------------------------
+  def _image(self, rows: int, k: int = LATENT) -> torch.Tensor:
+    return torch.empty([self._lib.gcb_a_image_bytes(max(rows, 1), k)], dtype=torch.uint8,
+                       device=self.device)
+
   def _alloc_workspace(self) -> None:
     m = self._model
     f = lambda rows, cols: torch.empty([max(rows, 1), cols], dtype=torch.float32, device=self.device)
     max_rows = max(m.num_grid, m.num_mesh, m.e_g2m, m.e_mesh, m.e_m2g)
     big_edges = max(m.e_g2m, m.e_m2g)
-    self.hidden = torch.empty([self._lib.gcb_a_image_bytes(max(max_rows, 1), LATENT)],
-                              dtype=torch.uint8, device=self.device)   # operand image
-    self.edge_a, self.edge_b = f(big_edges, LATENT), f(big_edges, LATENT)
-    self.grid_lat, self.mesh_lat = f(m.num_grid, LATENT), f(m.num_mesh, LATENT)
-    self.mesh_agg = f(m.num_mesh, LATENT)
-    self.mesh_edge, self.mesh_msg = f(m.e_mesh, LATENT), f(m.e_mesh, LATENT)
+    # operand images (bf16 hi/lo in tensor-core A layout) and fp32 masters
+    self.hidden = self._image(max_rows)
+    self.edge_a_img = self._image(big_edges)
+    self.edge_b = f(big_edges, LATENT)
     self.grid_in = f(m.num_grid, self.c_in_pad)
+    self.grid_in_img = self._image(m.num_grid, self.c_in_pad)
+    self.mesh_in_img = self._image(m.num_mesh, self.c_in_pad)
+    self.grid_lat, self.grid_lat_img = f(m.num_grid, LATENT), self._image(m.num_grid)
+    self.mesh_lat, self.mesh_lat_img = f(m.num_mesh, LATENT), self._image(m.num_mesh)
+    self.mesh_agg, self.mesh_agg_img = f(m.num_mesh, LATENT), self._image(m.num_mesh)
+    self.mesh_edge, self.mesh_edge_img = f(m.e_mesh, LATENT), self._image(m.e_mesh)
+    self.mesh_msg = f(m.e_mesh, LATENT)
+    self.grid_agg_img = self._image(m.num_grid)
     self.grid_out = f(m.num_grid, 256)
+    # static mesh-node encoder input as an image, built once
+    _native.check(self._lib.gcb_rows_to_image(self.mesh_in.data_ptr(), self.c_in_pad, 1, m.num_mesh,
+                                              self.c_in_pad, self.mesh_in_img.data_ptr(),
+                                              self._stream()), "gcb_rows_to_image")
+    for name in ("hidden", "edge_a_img", "edge_b", "grid_in_img", "mesh_in_img", "grid_lat",
+                 "grid_lat_img", "mesh_lat", "mesh_lat_img", "mesh_agg", "mesh_agg_img",
+                 "mesh_edge", "mesh_edge_img", "mesh_msg", "grid_agg_img"):
+      setattr(m, name, self._ptr(getattr(self, name)))
     if self.pregather:
       self.proj_grid = f(m.num_grid, LATENT)
       self.proj_mesh_a, self.proj_mesh_b = f(m.num_mesh, LATENT), f(m.num_mesh, LATENT)
       m.proj_grid = self._ptr(self.proj_grid)
       m.proj_mesh_a, m.proj_mesh_b = self._ptr(self.proj_mesh_a), self._ptr(self.proj_mesh_b)
-    m.hidden, m.edge_a, m.edge_b = self._ptr(self.hidden), self._ptr(self.edge_a), self._ptr(self.edge_b)
-    m.grid_lat, m.mesh_lat, m.mesh_agg = self._ptr(self.grid_lat), self._ptr(self.mesh_lat), self._ptr(self.mesh_agg)
-    m.mesh_edge, m.mesh_msg = self._ptr(self.mesh_edge), self._ptr(self.mesh_msg)
 
   def workspace_bytes(self) -> int:
-    ts = [self.hidden, self.edge_a, self.edge_b, self.grid_lat, self.mesh_lat, self.mesh_agg,
-          self.mesh_edge, self.mesh_msg, self.grid_in, self.grid_out]
+    ts = [self.hidden, self.edge_a_img, self.edge_b, self.grid_in, self.grid_in_img,
+          self.mesh_in_img, self.grid_lat, self.grid_lat_img, self.mesh_lat, self.mesh_lat_img,
+          self.mesh_agg, self.mesh_agg_img, self.mesh_edge, self.mesh_edge_img, self.mesh_msg,
+          self.grid_agg_img, self.grid_out]
     if self.pregather:
       ts += [self.proj_grid, self.proj_mesh_a, self.proj_mesh_b]
     return sum(t.numel() * t.element_size() for t in ts)

@@ -61,6 +61,10 @@ typedef struct {
   int32_t k;            /* padded width, multiple of 16 */
   int32_t k_valid;      /* real width (<= k, multiple of 4) */
   int32_t fan;          /* >= 1 */
+  /* Alternative source: an operand image (see below) of a [rows, k] matrix, identity
+   * rows.  When non-NULL, table/idx/ld/k_valid/fan are ignored and the K-steps of this
+   * segment are streamed by TMA bulk copies instead of the gather warps. */
+  const void* img;
 } gcb_segment;
 
 /* A gathered pre-activation addend:  y_pre[r, :] += table[(idx ? idx[r] : r), 0:n].
@@ -103,21 +107,24 @@ typedef struct {
   int32_t precision;    /* gcb_precision */
   int32_t n_pre_add;    /* 0..2; requires ln_scale == NULL and n_valid % 32 == 0 */
   gcb_pre_add pre_add[2];
-  /* Operand-image path.  An "A image" of a [rows, 512] fp32 matrix is its bf16 hi/lo
-   * split stored tile by tile in the exact shared-memory layout of the tensor-core A
-   * operand: for row tile t (128 rows) and K-step s (16 columns) a block of
-   * GCB_A_IMAGE_BLOCK bytes = [hi: 2 chunks x (128 rows x 16 B) with a 64 B skew | lo: same].
-   *   a_img   != NULL : the layer input is this image (segments ignored, K = a_img_k);
-   *                     it is streamed by TMA bulk copies -- no gather / conversion warps.
-   *   out_img != NULL : the layer output y (n = n_valid = 512) is ALSO written as an image,
-   *                     ready to be the a_img of the next layer.
-   * gcb_a_image_bytes(rows, k) gives the buffer size. */
-  const void* a_img; int32_t a_img_k;
+  /* Operand images.  The "A image" of a [rows, k] fp32 matrix is its bf16 hi/lo split
+   * stored tile by tile in the exact shared-memory layout of the tensor-core A operand:
+   * for row tile t (128 rows) and K-step s (16 columns) one block of GCB_A_IMAGE_BLOCK
+   * bytes = [hi: 2 chunks x (128 rows x 16 B), 64 B skew | lo: same], blocks ordered
+   * [t][s].  gcb_a_image_bytes(rows, k) gives the buffer size.
+   *   out_img != NULL : the layer result (out semantics: residual + y; n = n_valid = 512)
+   *                     is ALSO written as an image, ready to be a segment.img later. */
   void* out_img;
 } gcb_layer_desc;
 
 #define GCB_A_IMAGE_BLOCK 8448
 int64_t gcb_a_image_bytes(int64_t rows, int32_t k);
+
+/* img[r, 0:k] = sum_{j < fan} src[(r*fan + j), 0:k]  as an operand image (k multiple of
+ * 16, k <= ld).  fan = 1 converts an fp32 matrix; fan = 3 is the mesh2grid aggregation
+ * (jraph.segment_sum over the 3 incoming edges of a grid node, typed_graph_net.py:535-537). */
+int gcb_rows_to_image(const float* src, int32_t ld, int32_t fan, int64_t rows, int32_t k,
+                      void* img, void* stream);
 
 int gcb_abi_version(void);
 const char* gcb_last_error(void);
@@ -230,15 +237,20 @@ typedef struct {
   float* proj_mesh_a;       /* [num_mesh, 512] */
   float* proj_mesh_b;       /* [num_mesh, 512] */
 
-  /* workspace (fp32): */
-  void* hidden;       /* A image of [max_rows, 512] (gcb_a_image_bytes) */
-  float* edge_a;      /* [max(e_g2m,e_m2g), 512] */
-  float* edge_b;      /* [max(e_g2m,e_m2g), 512] */
-  float* grid_lat;    /* [num_grid, 512] latent grid nodes */
-  float* mesh_lat;    /* [num_mesh, 512] latent mesh nodes */
-  float* mesh_agg;    /* [num_mesh, 512] */
-  float* mesh_edge;   /* [e_mesh, 512] latent mesh edges */
-  float* mesh_msg;    /* [e_mesh, 512] */
+  /* workspace: fp32 masters (residual streams, gather tables, messages) and operand
+   * images (gcb_a_image_bytes) of everything that is consumed as an identity-row A
+   * operand -- those are streamed by TMA. */
+  void* hidden;         /* image [max_rows, 512]: hidden activations of the current MLP */
+  void* edge_a_img;     /* image [max(e_g2m,e_m2g), 512]: embedded bipartite edge latents */
+  float* edge_b;        /* [max(e_g2m,e_m2g), 512] bipartite messages */
+  void* grid_in_img;    /* image [num_grid, c_in_pad] */
+  const void* mesh_in_img;  /* image [num_mesh, c_in_pad] of mesh_in (static) */
+  float* grid_lat;  void* grid_lat_img;    /* [num_grid, 512] latent grid nodes */
+  float* mesh_lat;  void* mesh_lat_img;    /* [num_mesh, 512] latent mesh nodes */
+  float* mesh_agg;  void* mesh_agg_img;    /* [num_mesh, 512] segment sums */
+  float* mesh_edge; void* mesh_edge_img;   /* [e_mesh, 512] latent mesh edges */
+  float* mesh_msg;      /* [e_mesh, 512] */
+  void* grid_agg_img;   /* image [num_grid, 512]: summed mesh2grid messages */
 } gcb_model;
 
 /* One 6 h step for one batch element:
@@ -261,7 +273,7 @@ int gcb_forward(const gcb_model* m, const float* grid_in, float* grid_out, void*
  * bytes -- the caller adds edges*width*4).  Not thread safe. */
 typedef enum {
   GCB_KIND_LAYER_TC = 0, GCB_KIND_SEGMENT_SUM = 1, GCB_KIND_PACK = 2, GCB_KIND_UNPACK = 3,
-  GCB_KIND_LAYER_SIMT = 4
+  GCB_KIND_LAYER_SIMT = 4, GCB_KIND_ROWS_TO_IMAGE = 5
 } gcb_kernel_kind;
 int gcb_profile_begin(void);
 int gcb_profile_end(int32_t capacity, int32_t* kinds, float* ms, double* flops, double* bytes,

@@ -200,8 +200,8 @@ def test_operand_image_chain(prec, rows):
   d.precision = _native.PRECISIONS[prec]
   _native.check(lib.gcb_layer_forward(C.byref(d), st), "layer0")
   d1 = _native.LayerDesc()
-  d1.rows, d1.n, d1.n_valid, d1.nseg = rows, 512, 512, 0
-  d1.a_img, d1.a_img_k = himg.data_ptr(), 512
+  d1.rows, d1.n, d1.n_valid, d1.nseg = rows, 512, 512, 1
+  d1.seg[0].img, d1.seg[0].k = himg.data_ptr(), 512
   d1.w_packed, d1.w_f32, d1.bias = img1.data_ptr(), wf1.data_ptr(), b1d.data_ptr()
   d1.ln_scale, d1.ln_offset = scd.data_ptr(), ofd.data_ptr()
   d1.out, d1.ld_out = out.data_ptr(), 512
@@ -213,6 +213,72 @@ def test_operand_image_chain(prec, rows):
   y = torch.nn.functional.layer_norm(h @ w1.double() + b1.double(), (512,), sc.double(), of.double(), 1e-5)
   err = float((out.cpu().double() - y).abs().max() / y.abs().max())
   assert err < 2 * TOL[prec], err
+
+
+@pytest.mark.parametrize("prec", ["fp32_simt", "bf16x3"])
+def test_mixed_image_and_gathered_segments_with_residual_image(prec):
+  """[image segment | gathered fp32 segment], LayerNorm + residual, result delivered as
+  fp32 AND as an operand image (which must include the residual)."""
+  lib = _native.lib()
+  dev = torch.device("cuda:0")
+  rows = 1000
+  g = torch.Generator().manual_seed(9)
+  a0 = torch.randn(rows, 512, generator=g)
+  tab = torch.randn(222, 512, generator=g)
+  idx = torch.randint(0, 222, (rows,), generator=g, dtype=torch.int32)
+  w = torch.randn(1024, 512, generator=g) / np.sqrt(1024)
+  bias, sc, of = 0.1 * torch.randn(512, generator=g), 1 + 0.1 * torch.randn(512, generator=g), 0.1 * torch.randn(512, generator=g)
+  res = torch.randn(rows, 512, generator=g)
+  img, wf = _pack(lib, w.numpy(), 1024, 512, dev)
+  a0d, tabd, idxd, bd, scd, ofd, resd = (t.to(dev) for t in (a0, tab, idx, bias, sc, of, res))
+  st = torch.cuda.current_stream().cuda_stream
+  a0img = torch.zeros(lib.gcb_a_image_bytes(rows, 512), dtype=torch.uint8, device=dev)
+  _native.check(lib.gcb_rows_to_image(a0d.data_ptr(), 512, 1, rows, 512, a0img.data_ptr(), st), "to_image")
+  out = torch.empty(rows, 512, device=dev)
+  oimg = torch.zeros(lib.gcb_a_image_bytes(rows, 512), dtype=torch.uint8, device=dev)
+  d = _native.LayerDesc()
+  d.rows, d.n, d.n_valid, d.nseg = rows, 512, 512, 2
+  d.seg[0].img, d.seg[0].k = a0img.data_ptr(), 512
+  d.seg[1].table, d.seg[1].idx, d.seg[1].ld, d.seg[1].k, d.seg[1].k_valid, d.seg[1].fan = \
+      tabd.data_ptr(), idxd.data_ptr(), 512, 512, 512, 1
+  d.w_packed, d.w_f32, d.bias = img.data_ptr(), wf.data_ptr(), bd.data_ptr()
+  d.ln_scale, d.ln_offset = scd.data_ptr(), ofd.data_ptr()
+  d.residual, d.ld_res, d.out, d.ld_out, d.out_img = resd.data_ptr(), 512, out.data_ptr(), 512, oimg.data_ptr()
+  d.precision = _native.PRECISIONS[prec]
+  _native.check(lib.gcb_layer_forward(C.byref(d), st), "layer")
+  torch.cuda.synchronize()
+  z = torch.cat([a0.double(), tab.double()[idx.long()]], 1)
+  y = torch.nn.functional.layer_norm(z @ w.double() + bias.double(), (512,), sc.double(), of.double(), 1e-5)
+  want = y + res.double()
+  assert float((out.cpu().double() - want).abs().max() / want.abs().max()) < 2 * TOL[prec]
+  # decode the output image and compare with the fp32 output (bf16 hi+lo ~ 2^-17 relative)
+  blocks = oimg.cpu().numpy().view(np.uint16).reshape(-1, 32, 2, 2112)   # tile, kstep, hi|lo, halfwords
+  def part(p):
+    x = blocks[:, :, p, :].astype(np.uint32) << 16
+    x = x.view(np.float32).reshape(-1, 32, 2, 1056)[..., :1024].reshape(-1, 32, 2, 128, 8)
+    return x.transpose(0, 3, 1, 2, 4).reshape(-1, 512)                   # [tile*128, 512]
+  dec = (part(0) + part(1))[:rows]
+  np.testing.assert_allclose(dec, out.cpu().numpy(), rtol=2e-5, atol=2e-5)
+
+
+def test_rows_to_image_fan_in():
+  lib = _native.lib()
+  dev = torch.device("cuda:0")
+  rows, fan, k = 301, 3, 512
+  src = torch.randn(rows * fan, 516, device=dev)
+  img = torch.zeros(lib.gcb_a_image_bytes(rows, k), dtype=torch.uint8, device=dev)
+  _native.check(lib.gcb_rows_to_image(src.data_ptr(), 516, fan, rows, k, img.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream), "to_image")
+  torch.cuda.synchronize()
+  blocks = img.cpu().numpy().view(np.uint16).reshape(-1, 32, 2, 2112)
+  def part(p):
+    x = blocks[:, :, p, :].astype(np.uint32) << 16
+    x = x.view(np.float32).reshape(-1, 32, 2, 1056)[..., :1024].reshape(-1, 32, 2, 128, 8)
+    return x.transpose(0, 3, 1, 2, 4).reshape(-1, 512)
+  dec = part(0) + part(1)
+  want = src[:, :k].view(rows, fan, k).sum(1).cpu().numpy()
+  np.testing.assert_allclose(dec[:rows], want, rtol=2e-5, atol=2e-5)
+  assert np.all(dec[rows:] == 0)
 
 
 def test_zero_rows_is_a_noop():

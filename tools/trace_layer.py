@@ -29,7 +29,7 @@ def run(rows, k, n, ln, act, csize, out_y=False, residual=False, idx=False, pre=
   d.precision = 0
   if img_in:
     ai = torch.zeros(lib.gcb_a_image_bytes(rows, k), dtype=torch.uint8, device=dev)
-    d.a_img, d.a_img_k, d.nseg = ai.data_ptr(), k, 0
+    d.seg[0].img, d.seg[0].k, d.nseg = ai.data_ptr(), k, 1
   if img_out:
     oi = torch.zeros(lib.gcb_a_image_bytes(rows, n), dtype=torch.uint8, device=dev)
     d.out_img, d.out, = oi.data_ptr(), None
