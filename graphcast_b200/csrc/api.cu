@@ -369,25 +369,29 @@ int64_t gcb_packed_weight_bytes(int32_t k, int32_t n) {
 int gcb_pack_weight_host(const float* w, int32_t k_rows, int32_t n_cols, int32_t k, int32_t n,
                          void* dst) {
   GCB_CHECK_ARG(w != nullptr && dst != nullptr, "null pointer");
-  GCB_CHECK_ARG(k > 0 && k % 16 == 0 && n > 0 && n % 8 == 0, "k must be a multiple of 16, n of 8");
+  GCB_CHECK_ARG(k > 0 && k % 16 == 0 && n > 0 && n % 256 == 0, "k must be a multiple of 16, n of 256");
   GCB_CHECK_ARG(k_rows <= k && n_cols <= n && k_rows >= 0 && n_cols >= 0, "real shape exceeds padded shape");
+  // Image order: [K-step][256-column block h][hi | lo][K chunk c][256 rows][8 elements]:
+  // one contiguous 16 KB block per (K-step, h) = the B tile of one unit's K-step.
+  GCB_CHECK_ARG(n % 256 == 0, "n must be a multiple of 256");
   uint16_t* img = static_cast<uint16_t*>(dst);
-  const int ksteps = k / 16;
-  for (int ks = 0; ks < ksteps; ++ks) {
-    uint16_t* hi = img + static_cast<size_t>(ks) * n * 32;   // n*64 bytes per K-step
-    uint16_t* lo = hi + static_cast<size_t>(n) * 16;
-    for (int c = 0; c < 2; ++c)
-      for (int nn = 0; nn < n; ++nn)
-        for (int j = 0; j < 8; ++j) {
-          const int kk = ks * 16 + c * 8 + j;
-          const float v = (kk < k_rows && nn < n_cols) ? w[static_cast<size_t>(kk) * n_cols + nn] : 0.f;
-          const uint16_t h = f32_to_bf16_rne(v);
-          const uint16_t l = f32_to_bf16_rne(v - bf16_to_f32(h));
-          const size_t off = (static_cast<size_t>(c) * n + nn) * 8 + j;
-          hi[off] = h;
-          lo[off] = l;
-        }
-  }
+  const int ksteps = k / 16, halves = n / 256;
+  for (int ks = 0; ks < ksteps; ++ks)
+    for (int h = 0; h < halves; ++h) {
+      uint16_t* hi = img + (static_cast<size_t>(ks) * halves + h) * 8192;   // 16 KB per block
+      uint16_t* lo = hi + 4096;
+      for (int c = 0; c < 2; ++c)
+        for (int r = 0; r < 256; ++r)
+          for (int j = 0; j < 8; ++j) {
+            const int kk = ks * 16 + c * 8 + j, nn = h * 256 + r;
+            const float v = (kk < k_rows && nn < n_cols) ? w[static_cast<size_t>(kk) * n_cols + nn] : 0.f;
+            const uint16_t hv = f32_to_bf16_rne(v);
+            const uint16_t lv = f32_to_bf16_rne(v - bf16_to_f32(hv));
+            const size_t off = (static_cast<size_t>(c) * 256 + r) * 8 + j;
+            hi[off] = hv;
+            lo[off] = lv;
+          }
+    }
   return GCB_OK;
 }
 

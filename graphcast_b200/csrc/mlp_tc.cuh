@@ -1,34 +1,35 @@
 // Fused linear layer on tcgen05 tensor cores (sm_100a).
 //
-//   out[r] = residual[r] + LN( act( concat_s gather_s(r) @ W + bias ) )
+//   out[r] = residual[r] + LN( act( concat_s A_s(r) @ W + bias + gathered addends ) )
 //
-// One persistent CTA per SM processes 128-row tiles; the CTAs of a thread-block
-// cluster process consecutive tiles in lockstep and share the weight stream.
-// Warp roles:
-//   warp 0        weight producer: one lane streams 1/cluster of the pre-packed bf16
-//                 weight image of each K-step with cp.async.bulk (TMA engine),
-//                 multicast to every CTA of the cluster, completing on each CTA's
-//                 stage mbarrier (cuts L2->SM weight traffic by the cluster size).
-//   warp 1        MMA issuer: one lane issues tcgen05.mma (M=128, N=256 x n/256,
-//                 K=16) per stage -- three products per stage in BF16X3 mode
-//                 (hi*hi, hi*lo, lo*hi) -- accumulating fp32 in TMEM; commits
-//                 free the stage and finally publish the accumulator.
-//   warp 2        TMEM allocator (512 columns = 128 x 512 fp32 accumulator).
-//   warps 4-7     epilogue: tcgen05.ld the accumulator (thread = row), bias,
-//                 swish | LayerNorm (+ residual); 32x32 blocks are transposed through
-//                 shared memory so global stores / residual loads are full 128 B lines.
-//   warps 8-15    activation producers (two groups of four warps, alternating
-//                 K-steps): gather the fp32 rows of every K-segment through the
-//                 sender / receiver index (ld.global.v4), split to bf16 hi/lo and
-//                 store them into the stage in the UMMA K-major core-matrix
-//                 layout; the concatenated [E,1536] edge input is never
-//                 materialised.
+// One persistent 512-thread CTA per SM.  Work is cut into UNITS of 128 rows x 256 output
+// columns (a 128-row tile has n/256 units); TMEM holds TWO 128x256 fp32 accumulators, so
+// the epilogue of unit u overlaps the MMAs of unit u+1.  The CTAs of a thread-block
+// cluster walk consecutive tiles in lockstep and share the weight stream.  Warp roles:
+//   warp 0        TMA lane: per K-step streams (a) 1/cluster of the pre-packed bf16 weight
+//                 tile with cp.async.bulk, multicast to every CTA of the cluster, and (b)
+//                 the A block of segments that are stored as operand images.
+//   warp 1        MMA lane: tcgen05.mma (M=128, N=256, K=16), three products per K-step in
+//                 BF16X3 mode (hi*hi, hi*lo, lo*hi), fp32 accumulation in TMEM; commits free
+//                 the stage (cluster-wide) and finally publish the accumulator.
+//   warp 2        TMEM allocator (512 columns).
+//   warps 4-7     epilogue: tcgen05.ld (thread = row), bias, gathered pre-activation
+//                 addends, swish | LayerNorm (+ residual).  fp32 outputs go through a
+//                 32x32 shared-memory transpose (full 128-byte lines); operand-image
+//                 outputs are written straight from the row layout (512-byte warp stores).
+//                 LayerNorm needs the whole 512-wide row: statistics are accumulated over
+//                 both units of a tile while the second unit's MMAs run, then both halves
+//                 are normalised and their accumulators released one after the other.
+//   warps 8-15    two producer groups.  A segments given as fp32 tables (optionally
+//                 gathered through an index, optionally a fan-in sum) are converted to
+//                 bf16 hi/lo and stored in the UMMA K-major core-matrix layout; gathered
+//                 pre-activation addends (node projections of the split edge MLP) are
+//                 staged into shared memory in 32-column chunks.
 //
-// Shared-memory operand layout (no swizzle, K-major): a [R x 16] bf16 operand of
-// one K-step is two "K chunks" of 8 elements; chunk c, row r lives at byte
-// c * LBO + r*16.  Eight consecutive rows form one 128-byte core matrix, so
-// SBO = 128; LBO = N*16 for the weights and 128*16 + 64 for the activations
-// (see kALbo and ptx.cuh make_smem_desc).
+// Shared-memory operand layout (no swizzle, K-major): a [R x 16] bf16 operand of one
+// K-step is two "K chunks" of 8 elements; chunk c, row r lives at byte c*LBO + r*16.
+// Eight consecutive rows form one 128-byte core matrix, so SBO = 128; LBO = 256*16 for the
+// weights and 128*16 + 64 for the activations (see kALbo and ptx.cuh make_smem_desc).
 #pragma once
 #include "../../include/graphcast_b200.h"
 #include "ptx.cuh"
@@ -36,6 +37,7 @@
 namespace gcb {
 
 constexpr int kTileM = 128;
+constexpr int kUnitN = 256;                       // output columns per unit / accumulator
 constexpr int kKStep = 16;
 constexpr int kThreads = 512;
 // A operand: the two 8-element K chunks of a K-step are 2048 + 64 bytes apart.  The
@@ -43,10 +45,12 @@ constexpr int kThreads = 512;
 // stores (rows 0-3 of both chunks per half-warp) are conflict-free.
 constexpr int kALbo = kTileM * 16 + 64;           // 2112
 constexpr int kAPartBytes = 2 * kALbo;            // 4224: one of {hi, lo}
+constexpr int kBLbo = kUnitN * 16;                // 4096
+constexpr int kBPartBytes = 2 * kBLbo;            // 8192: one of {hi, lo} of a 256-row weight block
 constexpr int kEpiRowFloats = 36;                 // 32 + 4 pad: conflict-free 16 B accesses
 constexpr int kEpiStageBytes = 4 * 32 * kEpiRowFloats * 4;   // per-warp 32x32 transpose tiles
 // Pre-activation addend chunks (gathered node projections), double buffered:
-// [2][128 rows][36 floats], filled by producer group 1, read by the epilogue.
+// [2][128 rows][36 floats], filled by the producer groups, read by the epilogue.
 constexpr int kGBufFloats = kTileM * kEpiRowFloats;
 constexpr int kGBytes = 2 * kGBufFloats * 4;
 constexpr int kMaxN = 512;
@@ -56,12 +60,13 @@ static_assert(2 * kAPartBytes == GCB_A_IMAGE_BLOCK, "A image block must match th
 
 template <bool kSplit>
 struct TcConfig {
-  static constexpr int kStages = kSplit ? 4 : 8;
+  static constexpr int kStages = kSplit ? 6 : 10;
   static constexpr int kAStageBytes = kSplit ? 2 * kAPartBytes : kAPartBytes;
-  static constexpr int kBStageBytes = kSplit ? kMaxN * kKStep * 4 : kMaxN * kKStep * 2;
+  static constexpr int kBStageBytes = kSplit ? 2 * kBPartBytes : kBPartBytes;
   static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
   static constexpr int kParamBytes = 3 * kMaxN * 4;  // bias, ln scale, ln offset
-  static constexpr int kSmemBytes = kStages * kStageBytes + kParamBytes + kEpiStageBytes + kGBytes + 1024;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kParamBytes + kEpiStageBytes + kGBytes + 1024;
 };
 
 __device__ __forceinline__ float swish_f(float x) {
@@ -71,14 +76,14 @@ __device__ __forceinline__ float swish_f(float x) {
 }
 
 // Optional timeline trace (debug): when non-null, CTA 0 records clock64() at a few
-// points of each of its first kTraceTiles tiles; see gcb_debug_trace in api.cu.
+// points of each of its first kTraceTiles units; see gcb_debug_trace in api.cu.
 constexpr int kTraceTiles = 64;
 constexpr int kTraceEvents = 8;
 __device__ long long* g_trace = nullptr;
 
-__device__ __forceinline__ void trace(uint32_t tile_iter, int ev) {
-  if (g_trace != nullptr && blockIdx.x == 0 && tile_iter < kTraceTiles)
-    g_trace[tile_iter * kTraceEvents + ev] = clock64();
+__device__ __forceinline__ void trace(uint32_t unit, int ev) {
+  if (g_trace != nullptr && blockIdx.x == 0 && unit < kTraceTiles)
+    g_trace[unit * kTraceEvents + ev] = clock64();
 }
 
 struct KStepInfo {
@@ -117,9 +122,9 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
   uint8_t* tail = reinterpret_cast<uint8_t*>(s_g + 2 * kGBufFloats);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);          // [kStages]
   uint64_t* empty_bar = full_bar + Cfg::kStages;                   // [kStages]
-  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;              // [1]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 1;                    // [1]
-  uint64_t* g_full_bar = tmem_empty_bar + 1;                       // [2]
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;              // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;                    // [2]
+  uint64_t* g_full_bar = tmem_empty_bar + 2;                       // [2]
   uint64_t* g_empty_bar = g_full_bar + 2;                          // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(g_empty_bar + 2);
   SegInfo* s_seg = reinterpret_cast<SegInfo*>(tmem_base_slot + 2);        // [3]
@@ -129,9 +134,10 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n = d.n;
+  const int n_halves = n / kUnitN;             // units per 128-row tile (1 or 2)
   const int num_tiles = (d.rows + kTileM - 1) / kTileM;
   // Segments backed by an operand image are streamed by TMA; if every segment is,
-  // the gather warps have no A work at all (a_is_img).
+  // the producer warps have no A work at all (a_is_img).
   int ksteps = 0;
   bool a_is_img = true;
   for (int s = 0; s < d.nseg; ++s) {
@@ -139,7 +145,6 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
     a_is_img = a_is_img && (d.seg[s].img != nullptr);
   }
   uint8_t* const out_img = static_cast<uint8_t*>(d.out_img);
-  constexpr bool has_ln = kLN;
   // Descriptor fields used inside hot loops, hoisted into registers once.
   const long long rows_total = d.rows;
   const int nseg = d.nseg;
@@ -159,8 +164,8 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
   // ---- one-time setup ---------------------------------------------------------
   for (int i = threadIdx.x; i < n; i += kThreads) {
     s_bias[i] = d.bias[i];
-    s_scale[i] = has_ln ? d.ln_scale[i] : 1.0f;
-    s_offset[i] = has_ln ? d.ln_offset[i] : 0.0f;
+    s_scale[i] = kLN ? d.ln_scale[i] : 1.0f;
+    s_offset[i] = kLN ? d.ln_offset[i] : 0.0f;
   }
   if (threadIdx.x == 0) {
     int ks = 0;
@@ -186,15 +191,15 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
         ++ks;
       }
     for (int s = 0; s < Cfg::kStages; ++s) {
-      // 1 TMA lane (+ 4 activation-producer warps unless A comes from an image)
+      // 1 TMA lane (+ 4 activation-producer warps unless A comes from images only)
       ptx::mbar_init(&full_bar[s], a_is_img ? 1 : 5);
       ptx::mbar_init(&empty_bar[s], csize);  // tcgen05.commit of every CTA in the cluster
     }
-    ptx::mbar_init(tmem_full_bar, 1);
-    ptx::mbar_init(tmem_empty_bar, 4);   // 4 epilogue warps
     for (int b = 0; b < 2; ++b) {
-      ptx::mbar_init(&g_full_bar[b], 4);   // 4 warps of producer group 1
-      ptx::mbar_init(&g_empty_bar[b], 4);  // 4 epilogue warps
+      ptx::mbar_init(&tmem_full_bar[b], 1);
+      ptx::mbar_init(&tmem_empty_bar[b], 4);   // 4 epilogue warps
+      ptx::mbar_init(&g_full_bar[b], 4);       // 4 warps of one producer group
+      ptx::mbar_init(&g_empty_bar[b], 4);      // 4 epilogue warps
     }
     ptx::fence_mbar_init();
   }
@@ -210,153 +215,139 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
 
   // ---- roles ------------------------------------------------------------------
   if (warp == 0) {
-    // ===== weight producer =====
+    // ===== TMA lane =====
     if (lane == 0) {
-      const uint32_t b_bytes = static_cast<uint32_t>(n) * kKStep * (kSplit ? 4 : 2);
-      const size_t b_stride = static_cast<size_t>(n) * kKStep * 4;  // image always holds hi|lo
+      const uint32_t b_bytes = Cfg::kBStageBytes;                 // hi (| lo) of a 256-row block
+      const size_t b_block = 2 * kBPartBytes;                     // image always holds hi|lo
       const uint8_t* wimg = static_cast<const uint8_t*>(d.w_packed);
       const uint32_t slice = b_bytes / csize;
-      const uint32_t a_bytes = Cfg::kAStageBytes;            // hi (| lo) block of one K-step
+      const uint32_t a_bytes = Cfg::kAStageBytes;                 // hi (| lo) block of one K-step
       uint32_t it = 0;
       for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles); base += tile_stride) {
         const uint32_t tile = base + crank;
         const bool tile_ok = tile < static_cast<uint32_t>(num_tiles);   // else: dummy tile
-        for (int ks = 0; ks < ksteps; ++ks, ++it) {
-          const uint32_t stage = it % Cfg::kStages;
-          const uint32_t phase = (it / Cfg::kStages) & 1;
-          const KStepInfo ki = ks_info[ks];
-          const bool a_copy = tile_ok && ki.is_img;
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);     // free in every CTA of the cluster
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], b_bytes + (a_copy ? a_bytes : 0u));
-          if (a_copy) {
-            const SegInfo sg = s_seg[ki.seg];
-            ptx::bulk_g2s(stage_base + stage * Cfg::kStageBytes,
-                          sg.img + (static_cast<size_t>(tile) * sg.ksteps + (ki.koff >> 4)) *
-                                       GCB_A_IMAGE_BLOCK,
-                          a_bytes, &full_bar[stage]);
-          }
-          uint8_t* dst = stage_base + stage * Cfg::kStageBytes + Cfg::kAStageBytes;
-          const uint8_t* src = wimg + ks * b_stride;
-          if (csize == 1) {
-            ptx::bulk_g2s(dst, src, b_bytes, &full_bar[stage]);
-          } else {
-            // Each CTA fetches 1/csize of the tile and multicasts it to all of them.
-            ptx::bulk_g2s_multicast(dst + crank * slice, src + crank * slice, slice,
-                                    &full_bar[stage], cmask);
+        for (int h = 0; h < n_halves; ++h) {
+          for (int ks = 0; ks < ksteps; ++ks, ++it) {
+            const uint32_t stage = it % Cfg::kStages;
+            const uint32_t phase = (it / Cfg::kStages) & 1;
+            const KStepInfo ki = ks_info[ks];
+            const bool a_copy = tile_ok && ki.is_img;
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);   // free in every CTA of the cluster
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], b_bytes + (a_copy ? a_bytes : 0u));
+            if (a_copy) {
+              const SegInfo sg = s_seg[ki.seg];
+              ptx::bulk_g2s(stage_base + stage * Cfg::kStageBytes,
+                            sg.img + (static_cast<size_t>(tile) * sg.ksteps + (ki.koff >> 4)) *
+                                         GCB_A_IMAGE_BLOCK,
+                            a_bytes, &full_bar[stage]);
+            }
+            uint8_t* dst = stage_base + stage * Cfg::kStageBytes + Cfg::kAStageBytes;
+            const uint8_t* src = wimg + (static_cast<size_t>(ks) * n_halves + h) * b_block;
+            if (csize == 1) {
+              ptx::bulk_g2s(dst, src, b_bytes, &full_bar[stage]);
+            } else {
+              // Each CTA fetches 1/csize of the block and multicasts it to all of them.
+              ptx::bulk_g2s_multicast(dst + crank * slice, src + crank * slice, slice,
+                                      &full_bar[stage], cmask);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
+    // ===== MMA lane =====
     if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16(kTileM, 256);
-      const uint32_t n_halves = n / 256;
-      const uint32_t b_lbo = static_cast<uint32_t>(n) * 16;
-      const uint32_t b_part = static_cast<uint32_t>(n) * kKStep * 2;
-      uint32_t it = 0, tile_iter = 0;
-      for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles);
-           base += tile_stride, ++tile_iter) {
-        ptx::mbar_wait(tmem_empty_bar, (tile_iter & 1) ^ 1);
-        ptx::tc_fence_after_sync();
-        trace(tile_iter, 0);
-        for (int ks = 0; ks < ksteps; ++ks, ++it) {
-          const uint32_t stage = it % Cfg::kStages;
-          const uint32_t phase = (it / Cfg::kStages) & 1;
-          ptx::mbar_wait(&full_bar[stage], phase);
+      const uint32_t idesc = ptx::make_idesc_bf16(kTileM, kUnitN);
+      uint32_t it = 0, u = 0;
+      for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles); base += tile_stride) {
+        for (int h = 0; h < n_halves; ++h, ++u) {
+          const uint32_t buf = u & 1;
+          ptx::mbar_wait(&tmem_empty_bar[buf], ((u >> 1) & 1) ^ 1);
           ptx::tc_fence_after_sync();
-          if (ks == 0) trace(tile_iter, 1);
-          const uint32_t sa = ptx::smem_addr(stage_base + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kAStageBytes;
-          const uint64_t a_hi = ptx::make_smem_desc(sa, kALbo, 128);
-          const uint64_t a_lo = ptx::make_smem_desc(sa + kAPartBytes, kALbo, 128);
-          for (uint32_t h = 0; h < n_halves; ++h) {
-            const uint32_t boff = h * 256 * 16;
-            const uint64_t b_hi = ptx::make_smem_desc(sb + boff, b_lbo, 128);
-            const uint32_t dcol = tmem_base + h * 256;
+          trace(u, 0);
+          const uint32_t dcol = tmem_base + buf * kUnitN;
+          for (int ks = 0; ks < ksteps; ++ks, ++it) {
+            const uint32_t stage = it % Cfg::kStages;
+            const uint32_t phase = (it / Cfg::kStages) & 1;
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after_sync();
+            if (ks == 0) trace(u, 1);
+            const uint32_t sa = ptx::smem_addr(stage_base + stage * Cfg::kStageBytes);
+            const uint32_t sb = sa + Cfg::kAStageBytes;
+            const uint64_t a_hi = ptx::make_smem_desc(sa, kALbo, 128);
+            const uint64_t b_hi = ptx::make_smem_desc(sb, kBLbo, 128);
             ptx::mma_bf16_ss(dcol, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
             if (kSplit) {
-              const uint64_t b_lo = ptx::make_smem_desc(sb + b_part + boff, b_lbo, 128);
+              const uint64_t a_lo = ptx::make_smem_desc(sa + kAPartBytes, kALbo, 128);
+              const uint64_t b_lo = ptx::make_smem_desc(sb + kBPartBytes, kBLbo, 128);
               ptx::mma_bf16_ss(dcol, a_hi, b_lo, idesc, 1u);
               ptx::mma_bf16_ss(dcol, a_lo, b_hi, idesc, 1u);
             }
+            // stage reusable (cluster-wide) once these MMAs retire
+            if (csize == 1) ptx::mma_commit(&empty_bar[stage]);
+            else ptx::mma_commit_multicast(&empty_bar[stage], cmask);
           }
-          // stage reusable (cluster-wide) once these MMAs retire
-          if (csize == 1) ptx::mma_commit(&empty_bar[stage]);
-          else ptx::mma_commit_multicast(&empty_bar[stage], cmask);
+          ptx::mma_commit(&tmem_full_bar[buf]);          // accumulator complete
+          trace(u, 2);
         }
-        ptx::mma_commit(tmem_full_bar);          // accumulator complete
-        trace(tile_iter, 2);
       }
     }
   } else if (warp >= 4 && warp < 8) {
     // ===== epilogue =====
-    // tcgen05.ld hands each thread one accumulator ROW (32 consecutive columns per
-    // load).  Writing rows straight to global memory from that layout costs 32 cache
-    // lines per warp store, so every 32x32 block is transposed through a padded
-    // per-warp shared-memory tile: 8 lanes then cover one 128-byte row segment and a
-    // warp store writes four complete lines.
     const int ew = warp - 4;                     // == warp % 4: TMEM lane quarter
     const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
     const int n_valid = d.n_valid;
     float* my_epi = s_epi + ew * 32 * kEpiRowFloats;
     const int cg = lane & 7;                     // 16-byte column group inside the 32-col block
     const int rsub = lane >> 3;                  // row within a group of 4
-    uint32_t tile_iter = 0, g_count = 0;
-    for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles);
-         base += tile_stride, ++tile_iter) {
-      const long long row0 = static_cast<long long>(base + crank) * kTileM + ew * 32;
-      ptx::mbar_wait(tmem_full_bar, tile_iter & 1);
-      ptx::tc_fence_after_sync();
-      if (ew == 0 && lane == 0) trace(tile_iter, 3);
-      const uint32_t taddr = tmem_base + lane_base;
-      float mean = 0.f, rstd = 1.f;
-      if (has_ln) {
-        // Pass 1: shifted sums for mean / biased variance over the n_valid columns.
-        float shift = 0.f, s1 = 0.f, s2 = 0.f;
-        for (int c0 = 0; c0 < n_valid; c0 += 32) {
-          float v[32];
-          ptx::tmem_ld32(taddr + c0, v);
-          float b[32];
+    uint32_t g_count = 0;
+
+    // LayerNorm statistics of one unit: shifted sums over its valid columns.
+    auto stats_unit = [&](uint32_t taddr, int col_base, int ncols, float& shift, float& s1,
+                          float& s2, bool first) {
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        float v[32];
+        ptx::tmem_ld32(taddr + c0, v);
+        float b[32];
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(&b[4 * q]) = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * q);
-          if (c0 == 0) shift = v[0] + b[0];
-          if (c0 + 32 <= n_valid) {
-            float p1 = 0.f, p2 = 0.f, q1 = 0.f, q2 = 0.f;   // two chains for ILP
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(&b[4 * q]) =
+              *reinterpret_cast<const float4*>(s_bias + col_base + c0 + 4 * q);
+        if (first && c0 == 0) shift = v[0] + b[0];
+        if (c0 + 32 <= ncols) {
+          float p1 = 0.f, p2 = 0.f, q1 = 0.f, q2 = 0.f;   // two chains for ILP
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const float x0 = v[j] + b[j] - shift, x1 = v[j + 1] + b[j + 1] - shift;
-              p1 += x0; p2 = fmaf(x0, x0, p2);
-              q1 += x1; q2 = fmaf(x1, x1, q2);
-            }
-            s1 += p1 + q1; s2 += p2 + q2;
-          } else {
+          for (int j = 0; j < 32; j += 2) {
+            const float x0 = v[j] + b[j] - shift, x1 = v[j + 1] + b[j + 1] - shift;
+            p1 += x0; p2 = fmaf(x0, x0, p2);
+            q1 += x1; q2 = fmaf(x1, x1, q2);
+          }
+          s1 += p1 + q1; s2 += p2 + q2;
+        } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (c0 + j < n_valid) {
-                const float x = v[j] + b[j] - shift;
-                s1 += x;
-                s2 = fmaf(x, x, s2);
-              }
+          for (int j = 0; j < 32; ++j) {
+            if (c0 + j < ncols) {
+              const float x = v[j] + b[j] - shift;
+              s1 += x;
+              s2 = fmaf(x, x, s2);
             }
           }
         }
-        const float inv_n = 1.0f / static_cast<float>(n_valid);
-        const float m1 = s1 * inv_n;
-        mean = shift + m1;
-        const float var = fmaxf(s2 * inv_n - m1 * m1, 0.f);
-        rstd = rsqrtf(var + 1e-5f);
       }
-      if (ew == 0 && lane == 0) trace(tile_iter, 4);
-      // Pass 2 (or the only pass): finish, transpose, store.  Only one warp per SM
-      // sub-partition runs this, so nothing hides latency for it: the fast path is
-      // branch-free and batches its loads (residual rows are requested before the
-      // TMEM read, the eight shared-memory reads are issued back to back).
+    };
+
+    // Finish one unit: bias, addends, activation / normalisation, outputs.  Only one warp
+    // per SM sub-partition runs this, so nothing hides latency for it: the fast path is
+    // branch-free and batches its loads (residual rows are requested before the TMEM read,
+    // the eight shared-memory reads are issued back to back).
+    auto finish_unit = [&](uint32_t taddr, uint32_t tile, long long row0, int col_base, int ncols,
+                           float mean, float rstd) {
       const bool rows_full = row0 + 32 <= rows_total;
-      for (int c0 = 0; c0 < n_valid; c0 += 32) {
-        const int col = c0 + cg * 4;
-        const bool fast = rows_full && (c0 + 32 <= n_valid);
+      const bool tile_ok = tile < static_cast<uint32_t>(num_tiles);
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        const int gc0 = col_base + c0;             // global column of this 32-wide block
+        const int col = gc0 + cg * 4;
+        const bool fast = rows_full && (c0 + 32 <= ncols);
         float4 rr[8];
         if (fast && res_ptr != nullptr) {
 #pragma unroll
@@ -369,12 +360,12 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
           float b[32];
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(&b[4 * q]) = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * q);
+            *reinterpret_cast<float4*>(&b[4 * q]) = *reinterpret_cast<const float4*>(s_bias + gc0 + 4 * q);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += b[j];
         }
         if (!kLN && n_pre > 0) {
-          // Add the gathered node projections staged by producer group 1.
+          // Add the gathered node projections staged by the producer groups.
           const uint32_t gb = g_count & 1;
           ptx::mbar_wait(&g_full_bar[gb], (g_count >> 1) & 1);
           const float* gp = s_g + gb * kGBufFloats + (ew * 32 + lane) * kEpiRowFloats;
@@ -396,16 +387,18 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
           float g[32];
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(&g[4 * q]) = *reinterpret_cast<const float4*>(s_scale + c0 + 4 * q);
+            *reinterpret_cast<float4*>(&g[4 * q]) = *reinterpret_cast<const float4*>(s_scale + gc0 + 4 * q);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = (v[j] - mean) * rstd * g[j];
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(&g[4 * q]) = *reinterpret_cast<const float4*>(s_offset + c0 + 4 * q);
+            *reinterpret_cast<float4*>(&g[4 * q]) = *reinterpret_cast<const float4*>(s_offset + gc0 + 4 * q);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += g[j];
         }
         if (out_ptr != nullptr || outy_ptr != nullptr) {
+          // 32x32 transpose through the padded per-warp tile: 8 lanes then cover one
+          // 128-byte row segment and a warp store writes four complete lines.
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4*>(my_epi + lane * kEpiRowFloats + q * 4) =
@@ -413,22 +406,22 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
           __syncwarp();
           if (fast) {
             float4 y[8];
-  #pragma unroll
+#pragma unroll
             for (int i = 0; i < 8; ++i)
               y[i] = *reinterpret_cast<const float4*>(my_epi + (rsub + 4 * i) * kEpiRowFloats + cg * 4);
             if (outy_ptr != nullptr) {
-  #pragma unroll
+#pragma unroll
               for (int i = 0; i < 8; ++i)
                 *reinterpret_cast<float4*>(outy_ptr + (row0 + rsub + 4 * i) * ld_outy + col) = y[i];
             }
             if (out_ptr != nullptr) {
               if (res_ptr != nullptr) {
-  #pragma unroll
+#pragma unroll
                 for (int i = 0; i < 8; ++i) {
                   y[i].x += rr[i].x; y[i].y += rr[i].y; y[i].z += rr[i].z; y[i].w += rr[i].w;
                 }
               }
-  #pragma unroll
+#pragma unroll
               for (int i = 0; i < 8; ++i)
                 *reinterpret_cast<float4*>(out_ptr + (row0 + rsub + 4 * i) * ld_out + col) = y[i];
             }
@@ -444,7 +437,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
               const int r = rsub + 4 * i;
               const long long grow = row0 + r;
               if (grow < rows_total) {
-                for (int e = 0; e < 4 && col + e < n_valid; ++e) {
+                for (int e = 0; e < 4 && c0 + cg * 4 + e < ncols; ++e) {
                   const float yv = my_epi[r * kEpiRowFloats + cg * 4 + e];
                   const float ov = yv + (res_ptr ? res_ptr[grow * ld_res + col + e] : 0.f);
                   if (outy_ptr != nullptr) outy_ptr[grow * ld_outy + col + e] = yv;
@@ -454,7 +447,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
               }
             }
           }
-    __syncwarp();
+          __syncwarp();
           if (out_img != nullptr && res_ptr != nullptr) {
 #pragma unroll
             for (int q = 0; q < 8; ++q)
@@ -463,10 +456,10 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
             __syncwarp();
           }
         }
-        if (out_img != nullptr && (base + crank) < static_cast<uint32_t>(num_tiles)) {
-          // Operand image of this tile for the next layer: thread = row, so the 16-byte
+        if (out_img != nullptr && tile_ok) {
+          // Operand image of this tile for a later layer: thread = row, so the 16-byte
           // pieces of 32 consecutive rows are contiguous -> 512-byte coalesced warp stores.
-          uint8_t* blk = out_img + (static_cast<size_t>(base + crank) * (n >> 4) + (c0 >> 4)) * GCB_A_IMAGE_BLOCK +
+          uint8_t* blk = out_img + (static_cast<size_t>(tile) * (n >> 4) + (gc0 >> 4)) * GCB_A_IMAGE_BLOCK +
                          (ew * 32 + lane) * 16;
 #pragma unroll
           for (int ks2 = 0; ks2 < 2; ++ks2) {
@@ -483,14 +476,62 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
           }
         }
       }
-      if (ew == 0 && lane == 0) trace(tile_iter, 5);
+    };
+
+    auto release = [&](uint32_t buf) {
       ptx::tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tmem_empty_bar);
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
+    };
+
+    uint32_t u = 0;
+    for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles); base += tile_stride) {
+      const uint32_t tile = base + crank;
+      const long long row0 = static_cast<long long>(tile) * kTileM + ew * 32;
+      if (!kLN) {
+        for (int h = 0; h < n_halves; ++h, ++u) {
+          const uint32_t buf = u & 1;
+          ptx::mbar_wait(&tmem_full_bar[buf], (u >> 1) & 1);
+          ptx::tc_fence_after_sync();
+          if (ew == 0 && lane == 0) trace(u, 3);
+          const int col_base = h * kUnitN;
+          const int ncols = min(kUnitN, n_valid - col_base);
+          finish_unit(tmem_base + lane_base + buf * kUnitN, tile, row0, col_base, ncols, 0.f, 1.f);
+          if (ew == 0 && lane == 0) trace(u, 5);
+          release(buf);
+        }
+      } else {
+        // Statistics over all units of the row (overlapping the MMAs of the later ones),
+        // then normalise / store unit by unit, releasing each accumulator as soon as done.
+        float shift = 0.f, s1 = 0.f, s2 = 0.f;
+        const uint32_t u0 = u;
+        for (int h = 0; h < n_halves; ++h, ++u) {
+          const uint32_t buf = u & 1;
+          ptx::mbar_wait(&tmem_full_bar[buf], (u >> 1) & 1);
+          ptx::tc_fence_after_sync();
+          if (ew == 0 && lane == 0) trace(u, 3);
+          const int col_base = h * kUnitN;
+          stats_unit(tmem_base + lane_base + buf * kUnitN, col_base, min(kUnitN, n_valid - col_base),
+                     shift, s1, s2, h == 0);
+          if (ew == 0 && lane == 0) trace(u, 4);
+        }
+        const float inv_n = 1.0f / static_cast<float>(n_valid);
+        const float m1 = s1 * inv_n;
+        const float mean = shift + m1;
+        const float rstd = rsqrtf(fmaxf(s2 * inv_n - m1 * m1, 0.f) + 1e-5f);
+        for (int h = 0; h < n_halves; ++h) {
+          const uint32_t uu = u0 + h, buf = uu & 1;
+          const int col_base = h * kUnitN;
+          finish_unit(tmem_base + lane_base + buf * kUnitN, tile, row0, col_base,
+                      min(kUnitN, n_valid - col_base), mean, rstd);
+          if (ew == 0 && lane == 0) trace(uu, 5);
+          release(buf);
+        }
+      }
     }
   } else if (warp >= 8) {
-    // ===== activation producers =====
-    const int group = (warp - 8) >> 2;            // 0 or 1: alternating K-steps
+    // ===== producers =====
+    const int group = (warp - 8) >> 2;            // 0 or 1
     const int tid_g = threadIdx.x - 256 - group * 128;
     const int sub = tid_g & 3;                    // which float4 of the 16-wide K-step
     const int rg = tid_g >> 2;                    // 0..31; rows rg + 32*i
@@ -499,7 +540,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
     // With an image-fed A operand both groups gather (alternating chunks, one buffer
     // each); otherwise group 0 produces A and group 1 gathers.
     if (gather_mode && (a_is_img || group == 1)) {
-      // ===== pre-activation addend producer =====
+      // ----- pre-activation addend producer -----
       // Thread (rp, cgp): rows rp + 16*p (p < 8), 16-byte column group cgp of each 32-column
       // chunk: 8 lanes read one 128-byte line segment of a gathered row.
       const int cgp = tid_g & 7, rp = tid_g >> 3;
@@ -547,84 +588,87 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
         }
       }
     } else if (!a_is_img) {
-    uint32_t it = 0;
-    for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles); base += tile_stride) {
-      const uint32_t tile = base + crank;          // may be past the end: all-zero dummy tile
-      // Source row of each of my 4 tile rows, per segment (-1 = out of range).
-      long long src[3][4];
+      // ----- activation (A operand) producer -----
+      uint32_t it = 0;
+      for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles); base += tile_stride) {
+        const uint32_t tile = base + crank;          // may be past the end: all-zero dummy tile
+        // Source row of each of my 4 tile rows, per segment (-1 = out of range).
+        long long src[3][4];
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          src[s][i] = -1;
-          if (s < nseg) {
-            const long long grow = static_cast<long long>(tile) * kTileM + rg + 32 * i;
-            const int32_t* ip = s_seg[s].idx;
-            if (grow < rows_total) src[s][i] = ip ? static_cast<long long>(__ldg(ip + grow)) : grow;
-          }
-        }
-      }
-      float4 cur[4];
-      bool have_cur = false, cur_img = false;
-      uint32_t cur_it = 0;
-      // Software pipeline over the K-steps this group owns: the loads of the next
-      // owned K-step are in flight while the current one is converted and stored.
-      for (int ks = 0; ks <= ksteps; ++ks) {
-        const uint32_t this_it = it + ks;
-        // Normal mode: the two groups alternate K-steps.  Gather mode: group 0 owns all.
-        const bool mine = (ks < ksteps) && (gather_mode || (this_it & 1u) == static_cast<uint32_t>(group));
-        float4 nxt[4];
-        const bool img_step = mine && ks_info[ks].is_img;   // TMA brings the data: arrive only
-        if (mine && !img_step) {
-          const int s = ks_info[ks].seg;
-          const int koff = ks_info[ks].koff + sub * 4;
-          const SegInfo sg = s_seg[s];
-          const bool kvalid = koff < sg.k_valid;
+        for (int s = 0; s < 3; ++s) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            const long long sr = (s == 0) ? src[0][i] : (s == 1 ? src[1][i] : src[2][i]);
-            if (kvalid && sr >= 0) {
-              const float* p = sg.table + sr * sg.fan * sg.ld + koff;
-              acc = __ldg(reinterpret_cast<const float4*>(p));
-              for (int j = 1; j < sg.fan; ++j) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(p + static_cast<long long>(j) * sg.ld));
-                acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+            src[s][i] = -1;
+            if (s < nseg) {
+              const long long grow = static_cast<long long>(tile) * kTileM + rg + 32 * i;
+              const int32_t* ip = s_seg[s].idx;
+              if (grow < rows_total) src[s][i] = ip ? static_cast<long long>(__ldg(ip + grow)) : grow;
+            }
+          }
+        }
+        for (int h = 0; h < n_halves; ++h) {
+          float4 cur[4];
+          bool have_cur = false, cur_img = false;
+          uint32_t cur_it = 0;
+          // Software pipeline over the K-steps this group owns: the loads of the next
+          // owned K-step are in flight while the current one is converted and stored.
+          for (int ks = 0; ks <= ksteps; ++ks) {
+            const uint32_t this_it = it + ks;
+            // Normal mode: the two groups alternate K-steps.  Gather mode: group 0 owns all.
+            const bool mine = (ks < ksteps) && (gather_mode || (this_it & 1u) == static_cast<uint32_t>(group));
+            float4 nxt[4];
+            const bool img_step = mine && ks_info[ks].is_img;   // TMA brings the data: arrive only
+            if (mine && !img_step) {
+              const int s = ks_info[ks].seg;
+              const int koff = ks_info[ks].koff + sub * 4;
+              const SegInfo sg = s_seg[s];
+              const bool kvalid = koff < sg.k_valid;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                const long long sr = (s == 0) ? src[0][i] : (s == 1 ? src[1][i] : src[2][i]);
+                if (kvalid && sr >= 0) {
+                  const float* p = sg.table + sr * sg.fan * sg.ld + koff;
+                  acc = __ldg(reinterpret_cast<const float4*>(p));
+                  for (int j = 1; j < sg.fan; ++j) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(p + static_cast<long long>(j) * sg.ld));
+                    acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+                  }
+                }
+                nxt[i] = acc;
               }
             }
-            nxt[i] = acc;
-          }
-        }
-        if (have_cur && (mine || ks == ksteps)) {
-          const uint32_t stage = cur_it % Cfg::kStages;
-          const uint32_t phase = (cur_it / Cfg::kStages) & 1;
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* a_hi = stage_base + stage * Cfg::kStageBytes;
-          if (!cur_img) {
+            if (have_cur && (mine || ks == ksteps)) {
+              const uint32_t stage = cur_it % Cfg::kStages;
+              const uint32_t phase = (cur_it / Cfg::kStages) & 1;
+              ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* a_hi = stage_base + stage * Cfg::kStageBytes;
+              if (!cur_img) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint2 hi, lo;
-              ptx::split_bf16x4(cur[i], hi, lo);
-              const uint32_t off = sts_off + (rg + 32 * i) * 16;
-              *reinterpret_cast<uint2*>(a_hi + off) = hi;
-              if (kSplit) *reinterpret_cast<uint2*>(a_hi + kAPartBytes + off) = lo;
+                for (int i = 0; i < 4; ++i) {
+                  uint2 hi, lo;
+                  ptx::split_bf16x4(cur[i], hi, lo);
+                  const uint32_t off = sts_off + (rg + 32 * i) * 16;
+                  *reinterpret_cast<uint2*>(a_hi + off) = hi;
+                  if (kSplit) *reinterpret_cast<uint2*>(a_hi + kAPartBytes + off) = lo;
+                }
+              }
+              ptx::fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(&full_bar[stage]);
+              have_cur = false;
+            }
+            if (mine) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+              cur_it = this_it;
+              cur_img = img_step;
+              have_cur = true;
             }
           }
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&full_bar[stage]);
-          have_cur = false;
-        }
-        if (mine) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
-          cur_it = this_it;
-          cur_img = img_step;
-          have_cur = true;
+          it += ksteps;
         }
       }
-      it += ksteps;
-    }
     }
   }
 

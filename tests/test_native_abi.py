@@ -47,14 +47,21 @@ def test_pack_weight_host_layout_and_split_accuracy():
   assert lib.gcb_packed_weight_bytes(k, n) == k * n * 4
   img = np.zeros(k * n * 4, np.uint8)
   assert lib.gcb_pack_weight_host(w.ctypes.data, k_real, n_real, k, n, img.ctypes.data) == 0
-  im = img.view(np.uint16).reshape(k // 16, 2, 2, n, 8)      # kstep, hi|lo, chunk, n, j
-  hi, lo = _bf16_to_f32(im[:, 0]), _bf16_to_f32(im[:, 1])
-  rec = (hi + lo).transpose(0, 1, 3, 2).reshape(k, n)         # [kstep, chunk, j, n] -> [k, n]
+  im = img.view(np.uint16).reshape(k // 16, n // 256, 2, 2, 256, 8)   # kstep, block, hi|lo, chunk, row, j
+  hi, lo = _bf16_to_f32(im[:, :, 0]), _bf16_to_f32(im[:, :, 1])        # [ks, h, c, r, j]
+  rec = (hi + lo).transpose(0, 2, 4, 1, 3).reshape(k, n)               # [ks, c, j, h, r] -> [k, n]
   np.testing.assert_allclose(rec[:k_real, :n_real], w, rtol=2 ** -16, atol=1e-30)
   assert np.all(rec[k_real:] == 0) and np.all(rec[:, n_real:] == 0)
   # hi is the round-to-nearest-even bf16 of w
   want_hi = (((w.view(np.uint32) + 0x7fff + ((w.view(np.uint32) >> 16) & 1)) >> 16) << 16).view(np.float32)
-  np.testing.assert_array_equal(hi.transpose(0, 1, 3, 2).reshape(k, n)[:k_real, :n_real], want_hi)
+  np.testing.assert_array_equal(hi.transpose(0, 2, 4, 1, 3).reshape(k, n)[:k_real, :n_real], want_hi)
+  # 512-wide layer: two 256-column blocks per K-step
+  w2 = np.random.default_rng(1).standard_normal((32, 512)).astype(np.float32)
+  img2 = np.zeros(32 * 512 * 4, np.uint8)
+  assert lib.gcb_pack_weight_host(w2.ctypes.data, 32, 512, 32, 512, img2.ctypes.data) == 0
+  im2 = img2.view(np.uint16).reshape(2, 2, 2, 2, 256, 8)
+  rec2 = (_bf16_to_f32(im2[:, :, 0]) + _bf16_to_f32(im2[:, :, 1])).transpose(0, 2, 4, 1, 3).reshape(32, 512)
+  np.testing.assert_allclose(rec2, w2, rtol=2 ** -16, atol=1e-30)
   assert lib.gcb_pack_weight_host(w.ctypes.data, k_real, n_real, 24, n, img.ctypes.data) == -1
   assert b"multiple of 16" in lib.gcb_last_error()
 
