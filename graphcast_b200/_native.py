@@ -62,6 +62,7 @@ class Model(C.Structure):
       ("c_in_pad", C.c_int32), ("c_in_valid", C.c_int32),
       ("msg_steps", C.c_int32), ("precision", C.c_int32), ("pregather", C.c_int32),
       ("g2m_snd", _fp), ("g2m_rcv", _fp), ("g2m_row_ptr", _fp), ("g2m_feat", _fp),
+      ("g2m_heavy", _fp), ("n_g2m_heavy", C.c_int32),
       ("mesh_snd", _fp), ("mesh_rcv", _fp), ("mesh_row_ptr", _fp), ("mesh_feat", _fp),
       ("m2g_snd", _fp), ("m2g_rcv", _fp), ("m2g_feat", _fp),
       ("mesh_in", _fp),
@@ -74,8 +75,7 @@ class Model(C.Structure):
       ("proc_e_g2m_split", MlpSplit), ("proc_e_m2g_split", MlpSplit),
       ("proc_e_mesh_split", MlpSplit * GCB_MAX_MSG_STEPS),
       ("zero_bias", _fp), ("proj_grid", _fp), ("proj_mesh_a", _fp), ("proj_mesh_b", _fp),
-      ("hidden", _fp), ("edge_a_img", _fp), ("edge_b", _fp), ("grid_in_img", _fp),
-      ("mesh_in_img", _fp), ("grid_lat", _fp), ("grid_lat_img", _fp), ("mesh_lat", _fp),
+      ("hidden", _fp), ("edge_a_img", _fp), ("edge_b", _fp), ("mesh_in_img", _fp), ("grid_lat", _fp), ("grid_lat_img", _fp), ("mesh_lat", _fp),
       ("mesh_lat_img", _fp), ("mesh_agg", _fp), ("mesh_agg_img", _fp), ("mesh_edge", _fp),
       ("mesh_edge_img", _fp), ("mesh_msg", _fp), ("grid_agg_img", _fp),
   ]
@@ -92,8 +92,12 @@ EXPORTS = {
     "gcb_pack_weight_host": (C.c_int, [_fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _fp]),
     "gcb_layer_forward": (C.c_int, [C.POINTER(LayerDesc), _fp]),
     "gcb_segment_sum": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, _fp, C.c_int32, C.c_int32, _fp]),
+    "gcb_segment_sum_heavy": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, _fp, C.c_int32, _fp,
+                                        C.c_int32, C.c_int32, _fp]),
     "gcb_pack_grid_features": (C.c_int, [_fp, C.c_int32, C.c_int64, _fp, _fp, _fp, C.c_int32,
                                          _fp, C.c_int32, _fp]),
+    "gcb_pack_grid_image": (C.c_int, [_fp, C.c_int32, C.c_int64, _fp, _fp, _fp, C.c_int32,
+                                      C.c_int32, _fp, _fp]),
     "gcb_unpack_grid_outputs": (C.c_int, [_fp, C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp,
                                           _fp, _fp, _fp]),
     "gcb_forward": (C.c_int, [C.POINTER(Model), _fp, _fp, _fp, C.POINTER(C.c_int32)]),

@@ -189,7 +189,10 @@ int launch_tc_variant(const gcb_layer_desc& d, cudaStream_t stream) {
     max_clusters[dev][csize] = nc;
   }
   const int tiles = (d.rows + gcb::kTileM - 1) / gcb::kTileM;
-  int clusters = (tiles + csize - 1) / csize;
+  // N-split schedule (n = 512, cluster of 2): one tile per cluster at a time; otherwise
+  // every CTA of the cluster has its own tile.
+  const bool nsplit = (csize == 2 && d.n == 512);
+  int clusters = nsplit ? tiles : (tiles + csize - 1) / csize;
   if (clusters > max_clusters[dev][csize]) clusters = max_clusters[dev][csize];
   cfg.gridDim = dim3(clusters * csize);
   GCB_CUDA(cudaLaunchKernelEx(&cfg, kernel, d));
@@ -423,7 +426,14 @@ int gcb_layer_forward(const gcb_layer_desc* d, void* stream) {
 
 int gcb_segment_sum(const float* msg, int32_t ld_msg, const int32_t* row_ptr, int32_t num_nodes,
                     float* out, int32_t ld_out, int32_t width, void* stream) {
+  return gcb_segment_sum_heavy(msg, ld_msg, row_ptr, num_nodes, nullptr, 0, out, ld_out, width, stream);
+}
+
+int gcb_segment_sum_heavy(const float* msg, int32_t ld_msg, const int32_t* row_ptr,
+                          int32_t num_nodes, const int32_t* heavy, int32_t num_heavy, float* out,
+                          int32_t ld_out, int32_t width, void* stream) {
   GCB_CHECK_ARG(msg && row_ptr && out, "null pointer");
+  GCB_CHECK_ARG(num_heavy >= 0 && (num_heavy == 0 || heavy != nullptr), "heavy list is null");
   GCB_CHECK_ARG(width == 512, "segment_sum supports width 512");
   GCB_CHECK_ARG(ld_msg % 4 == 0 && ld_out % 4 == 0 && aligned16(msg) && aligned16(out), "unaligned");
   if (num_nodes == 0) return GCB_OK;
@@ -433,8 +443,9 @@ int gcb_segment_sum(const float* msg, int32_t ld_msg, const int32_t* row_ptr, in
   if (blocks > cap) blocks = cap;
   ProfScope prof(static_cast<cudaStream_t>(stream), GCB_KIND_SEGMENT_SUM, 0.0,
                  4.0 * width * (static_cast<double>(num_nodes) + 0.0) + 0.0);
-  gcb::segment_sum_kernel<4><<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      msg, ld_msg, row_ptr, num_nodes, out, ld_out);
+  gcb::segment_sum_kernel<4><<<static_cast<int>(blocks) + num_heavy, 256, 0,
+                              static_cast<cudaStream_t>(stream)>>>(
+      msg, ld_msg, row_ptr, num_nodes, out, ld_out, heavy, num_heavy);
   GCB_CUDA(cudaGetLastError());
   return GCB_OK;
 }
@@ -451,6 +462,31 @@ int gcb_pack_grid_features(const float* planes, int32_t n_ch, int64_t n_nodes, c
                  4.0 * n_nodes * (static_cast<double>(n_ch) + n_static + ld));
   gcb::pack_grid_features_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       planes, n_ch, n_nodes, mean, scale, node_static, n_static, feats, ld);
+  GCB_CUDA(cudaGetLastError());
+  return GCB_OK;
+}
+
+int gcb_pack_grid_image(const float* planes, int32_t n_ch, int64_t n_nodes, const float* mean,
+                        const float* scale, const float* node_static, int32_t n_static,
+                        int32_t k, void* img, void* stream) {
+  GCB_CHECK_ARG(planes && img && aligned16(img), "null/unaligned pointer");
+  GCB_CHECK_ARG(n_ch > 0 && n_static >= 0 && k % 16 == 0 && k >= n_ch + n_static, "k too small");
+  GCB_CHECK_ARG(n_static == 0 || node_static != nullptr, "node_static is null");
+  if (n_nodes == 0) return GCB_OK;
+  const size_t smem = 32 * static_cast<size_t>(k + 4) * sizeof(float);
+  GCB_CHECK_ARG(smem <= 96 * 1024, "k too large");
+  static bool attr_set = false;
+  if (!attr_set) {
+    GCB_CUDA(cudaFuncSetAttribute(gcb::pack_grid_image_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  const long long padded = (n_nodes + 127) / 128 * 128;
+  ProfScope prof(static_cast<cudaStream_t>(stream), GCB_KIND_PACK, 0.0,
+                 4.0 * n_nodes * (static_cast<double>(n_ch) + n_static + k));
+  gcb::pack_grid_image_kernel<<<static_cast<unsigned>(padded / 32), 256, smem,
+                                static_cast<cudaStream_t>(stream)>>>(
+      planes, n_ch, n_nodes, mean, scale, node_static, n_static, k, static_cast<unsigned char*>(img));
   GCB_CUDA(cudaGetLastError());
   return GCB_OK;
 }
@@ -494,12 +530,12 @@ int gcb_rows_to_image(const float* src, int32_t ld, int32_t fan, int64_t rows, i
   return GCB_OK;
 }
 
-int gcb_forward(const gcb_model* m, const float* grid_in, float* grid_out, void* stream,
+int gcb_forward(const gcb_model* m, const void* grid_in_img, float* grid_out, void* stream,
                 int32_t* launches) {
-  GCB_CHECK_ARG(m && grid_in && grid_out, "null pointer");
+  GCB_CHECK_ARG(m && grid_in_img && grid_out, "null pointer");
   GCB_CHECK_ARG(m->msg_steps >= 1 && m->msg_steps <= GCB_MAX_MSG_STEPS, "msg_steps out of range");
   GCB_CHECK_ARG(m->e_m2g == 3 * m->num_grid, "mesh2grid must have fan-in 3");
-  GCB_CHECK_ARG(m->hidden && m->edge_a_img && m->edge_b && m->grid_in_img && m->mesh_in_img &&
+  GCB_CHECK_ARG(m->hidden && m->edge_a_img && m->edge_b && m->mesh_in_img &&
                     m->grid_lat && m->grid_lat_img && m->mesh_lat && m->mesh_lat_img &&
                     m->mesh_agg && m->mesh_agg_img && m->mesh_edge && m->mesh_edge_img &&
                     m->mesh_msg && m->grid_agg_img,
@@ -515,8 +551,7 @@ int gcb_forward(const gcb_model* m, const float* grid_in, float* grid_out, void*
 
   // ---------------- encoder: grid2mesh_gnn (graphcast.py:550-604) ----------------
   // vg0 = LN.MLP(grid_in)  -> grid_lat (+ image)
-  if ((rc = to_image(c, grid_in, m->c_in_pad, 1, m->num_grid, m->c_in_pad, m->grid_in_img))) return rc;
-  s[0] = seg_img(m->grid_in_img, m->c_in_pad);
+  s[0] = seg_img(grid_in_img, m->c_in_pad);
   o = MlpOut(); o.out = m->grid_lat; o.out_img = m->grid_lat_img;
   if ((rc = run_mlp(c, m->enc_grid, m->num_grid, 1, s, o))) return rc;
   // vm0 = LN.MLP(mesh_in)  -> mesh_lat (+ image)
@@ -534,7 +569,8 @@ int gcb_forward(const gcb_model* m, const float* grid_in, float* grid_out, void*
                          m->mesh_lat, m->mesh_lat_img, m->num_mesh, m->g2m_rcv, m->proj_mesh_a, o)))
     return rc;
   // agg1 = segment_sum(m1)
-  if ((rc = gcb_segment_sum(m->edge_b, D, m->g2m_row_ptr, m->num_mesh, m->mesh_agg, D, D, stream))) return rc;
+  if ((rc = gcb_segment_sum_heavy(m->edge_b, D, m->g2m_row_ptr, m->num_mesh, m->g2m_heavy,
+                                  m->n_g2m_heavy, m->mesh_agg, D, D, stream))) return rc;
   c.launches += 1;
   if ((rc = to_image(c, m->mesh_agg, D, 1, m->num_mesh, D, m->mesh_agg_img))) return rc;
   // vm1 = vm0 + LN.MLP([vm0 | agg1])  (in place)

@@ -10,16 +10,56 @@ namespace gcb {
 // One warp per receiver node; lane l owns float4 columns l, l+32, ... so every
 // edge row is read with fully coalesced 512-byte warp loads and each output row
 // is written once -- no atomics, deterministic order.
+//
+// Receivers with more than kHeavyDegree in-edges (the mesh nodes next to the poles collect
+// thousands of grid points) would serialise one warp for milliseconds; they are listed in
+// `heavy` and handled by the last `num_heavy` blocks, one block per node: eight warps sum
+// contiguous slices of the node's edges and combine them in a fixed order (still
+// deterministic).
+constexpr int kHeavyDegree = 256;
+
 template <int kVecPerLane>
 __global__ void __launch_bounds__(256)
 segment_sum_kernel(const float* __restrict__ msg, int ld_msg, const int* __restrict__ row_ptr,
-                   int num_nodes, float* __restrict__ out, int ld_out) {
+                   int num_nodes, float* __restrict__ out, int ld_out,
+                   const int* __restrict__ heavy, int num_heavy) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
+  const int light_blocks = gridDim.x - num_heavy;
+  if (static_cast<int>(blockIdx.x) >= light_blocks) {
+    // ---- one block per heavy receiver ----
+    __shared__ float4 part[8][32 * kVecPerLane];
+    const int node = heavy[blockIdx.x - light_blocks];
+    const int beg = row_ptr[node], end = row_ptr[node + 1];
+    const int w = threadIdx.x >> 5;
+    const int per = (end - beg + 7) / 8;
+    const int lo = beg + w * per, hi = min(end, lo + per);
+    float4 acc[kVecPerLane];
+#pragma unroll
+    for (int j = 0; j < kVecPerLane; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = lo; e < hi; ++e) {
+      const float4* pa = reinterpret_cast<const float4*>(msg + static_cast<long long>(e) * ld_msg);
+#pragma unroll
+      for (int j = 0; j < kVecPerLane; ++j) {
+        const float4 a = __ldg(pa + lane + 32 * j);
+        acc[j].x += a.x; acc[j].y += a.y; acc[j].z += a.z; acc[j].w += a.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kVecPerLane; ++j) part[w][lane + 32 * j] = acc[j];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * kVecPerLane; i += blockDim.x) {
+      float4 s = part[0][i];
+      for (int k = 1; k < 8; ++k) { s.x += part[k][i].x; s.y += part[k][i].y; s.z += part[k][i].z; s.w += part[k][i].w; }
+      reinterpret_cast<float4*>(out + static_cast<long long>(node) * ld_out)[i] = s;
+    }
+    return;
+  }
   const long long gwarp = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
-  const long long nwarps = static_cast<long long>(gridDim.x) * warps_per_block;
+  const long long nwarps = static_cast<long long>(light_blocks) * warps_per_block;
   for (long long node = gwarp; node < num_nodes; node += nwarps) {
     const int beg = row_ptr[node], end = row_ptr[node + 1];
+    if (num_heavy > 0 && end - beg > kHeavyDegree) continue;   // done by a heavy block
     float4 acc[kVecPerLane];
 #pragma unroll
     for (int j = 0; j < kVecPerLane; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -83,6 +123,61 @@ pack_grid_features_kernel(const float* __restrict__ planes, int n_ch, long long 
     const long long node = node0 + r;
     const int c = c0 + tx;
     if (node < n_nodes && c < ld) feats[node * ld + c] = tile[tx][r];
+  }
+}
+
+// planes [n_ch, n_nodes] (+ node_static) -> operand image of the packed, normalised feature
+// rows [n_nodes, k] (k = padded channel count, multiple of 16): the fp32 feature matrix is
+// never materialised.  A block handles 32 nodes: phase 1 reads every channel plane with
+// 128-byte coalesced loads into a shared tile, phase 2 lets lane = node emit the 16-byte
+// image pieces (512-byte warp stores), as in rows_to_image_kernel.
+__global__ void __launch_bounds__(256)
+pack_grid_image_kernel(const float* __restrict__ planes, int n_ch, long long n_nodes,
+                       const float* __restrict__ mean, const float* __restrict__ scale,
+                       const float* __restrict__ node_static, int n_static, int k,
+                       unsigned char* __restrict__ img) {
+  extern __shared__ float tile[];                 // [32][k + 4]
+  const int kp = k + 4;
+  const long long node0 = static_cast<long long>(blockIdx.x) * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long node = node0 + lane;
+  for (int c = warp; c < k; c += 8) {
+    float v = 0.f;
+    if (node < n_nodes) {
+      if (c < n_ch) {
+        v = planes[static_cast<long long>(c) * n_nodes + node];
+        if (mean) v -= mean[c];
+        if (scale) v /= scale[c];
+      } else if (c < n_ch + n_static) {
+        v = node_static[node * n_static + (c - n_ch)];
+      }
+    }
+    tile[lane * kp + c] = v;
+  }
+  __syncthreads();
+  const long long t = node >> 7;
+  const int r = static_cast<int>(node & 127);
+  const int ksteps = k >> 4;
+  for (int piece = warp; piece < ksteps * 2; piece += 8) {
+    const int ks = piece >> 1, c = piece & 1;
+    const float* x = tile + lane * kp + ks * 16 + c * 8;
+    const float4 a = *reinterpret_cast<const float4*>(x), b = *reinterpret_cast<const float4*>(x + 4);
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    const float2 f2 = __bfloat1622float2(h2), f3 = __bfloat1622float2(h3);
+    __nv_bfloat162 l0 = __floats2bfloat162_rn(a.x - f0.x, a.y - f0.y), l1 = __floats2bfloat162_rn(a.z - f1.x, a.w - f1.y);
+    __nv_bfloat162 l2 = __floats2bfloat162_rn(b.x - f2.x, b.y - f2.y), l3 = __floats2bfloat162_rn(b.z - f3.x, b.w - f3.y);
+    if (node < ((n_nodes + 127) >> 7 << 7)) {
+      unsigned char* dst = img + (static_cast<size_t>(t) * ksteps + ks) * 8448 + c * 2112 + r * 16;
+      uint4 hv, lv;
+      hv.x = *reinterpret_cast<unsigned int*>(&h0); hv.y = *reinterpret_cast<unsigned int*>(&h1);
+      hv.z = *reinterpret_cast<unsigned int*>(&h2); hv.w = *reinterpret_cast<unsigned int*>(&h3);
+      lv.x = *reinterpret_cast<unsigned int*>(&l0); lv.y = *reinterpret_cast<unsigned int*>(&l1);
+      lv.z = *reinterpret_cast<unsigned int*>(&l2); lv.w = *reinterpret_cast<unsigned int*>(&l3);
+      *reinterpret_cast<uint4*>(dst) = hv;
+      *reinterpret_cast<uint4*>(dst + 4224) = lv;
+    }
   }
 }
 

@@ -3,9 +3,16 @@
 //   out[r] = residual[r] + LN( act( concat_s A_s(r) @ W + bias + gathered addends ) )
 //
 // One persistent 512-thread CTA per SM.  Work is cut into UNITS of 128 rows x 256 output
-// columns (a 128-row tile has n/256 units); TMEM holds TWO 128x256 fp32 accumulators, so
-// the epilogue of unit u overlaps the MMAs of unit u+1.  The CTAs of a thread-block
-// cluster walk consecutive tiles in lockstep and share the weight stream.  Warp roles:
+// columns; TMEM holds TWO 128x256 fp32 accumulators, so the epilogue of unit u overlaps
+// the MMAs of unit u+1.  Two schedules:
+//   N-split (n = 512, cluster of 2): both CTAs of the cluster work on the SAME 128-row
+//     tile, CTA r owning output columns [256r, 256r+256).  The A block of every K-step is
+//     fetched once and multicast to both CTAs, each CTA streams only its half of the
+//     weights, and LayerNorm row statistics are combined across the pair through
+//     distributed shared memory.  Consecutive units of a CTA are consecutive tiles.
+//   unsplit (n = 256, or cluster of 1): every CTA walks its own tiles (n/256 units per
+//     tile); the CTAs of a cluster share the weight stream by multicast.
+// Warp roles:
 //   warp 0        TMA lane: per K-step streams (a) 1/cluster of the pre-packed bf16 weight
 //                 tile with cp.async.bulk, multicast to every CTA of the cluster, and (b)
 //                 the A block of segments that are stored as operand images.
@@ -126,10 +133,14 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;                    // [2]
   uint64_t* g_full_bar = tmem_empty_bar + 2;                       // [2]
   uint64_t* g_empty_bar = g_full_bar + 2;                          // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(g_empty_bar + 2);
+  uint64_t* lnx_bar = g_empty_bar + 2;                             // [2] LayerNorm pair exchange
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(lnx_bar + 2);
   SegInfo* s_seg = reinterpret_cast<SegInfo*>(tmem_base_slot + 2);        // [3]
   PreAddInfo* s_pre = reinterpret_cast<PreAddInfo*>(s_seg + 3);           // [2]
   KStepInfo* ks_info = reinterpret_cast<KStepInfo*>(s_pre + 2);           // [kMaxKSteps]
+  // [2][128] LayerNorm statistics received from the partner CTA (N-split).  Aliases the
+  // addend buffers, which LayerNorm layers never use (pre_add excludes LayerNorm).
+  float2* s_lnx = reinterpret_cast<float2*>(s_g);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -157,8 +168,12 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
   // tiles in lockstep and share every weight tile through TMA multicast.
   const uint32_t crank = ptx::cluster_ctarank();
   const uint32_t csize = ptx::cluster_nctarank();
-  const uint32_t tile_first = ptx::cluster_id_x() * csize;
-  const uint32_t tile_stride = ptx::num_clusters_x() * csize;
+  const bool nsplit = (csize == 2) && (n_halves == 2);
+  const uint32_t tiles_per_iter = nsplit ? 1u : csize;       // tiles a cluster covers per iteration
+  const uint32_t tile_first = ptx::cluster_id_x() * tiles_per_iter;
+  const uint32_t tile_stride = ptx::num_clusters_x() * tiles_per_iter;
+  const uint32_t tile_off = nsplit ? 0u : crank;             // my tile = base + tile_off
+  const int units_per_tile = nsplit ? 1 : n_halves;          // units this CTA runs per tile
   const uint16_t cmask = static_cast<uint16_t>((1u << csize) - 1u);
 
   // ---- one-time setup ---------------------------------------------------------
@@ -200,6 +215,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
       ptx::mbar_init(&tmem_empty_bar[b], 4);   // 4 epilogue warps
       ptx::mbar_init(&g_full_bar[b], 4);       // 4 warps of one producer group
       ptx::mbar_init(&g_empty_bar[b], 4);      // 4 epilogue warps
+      ptx::mbar_init(&lnx_bar[b], 128);        // every epilogue thread of the partner CTA
     }
     ptx::fence_mbar_init();
   }
@@ -224,9 +240,10 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
       const uint32_t a_bytes = Cfg::kAStageBytes;                 // hi (| lo) block of one K-step
       uint32_t it = 0;
       for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles); base += tile_stride) {
-        const uint32_t tile = base + crank;
+        const uint32_t tile = base + tile_off;
         const bool tile_ok = tile < static_cast<uint32_t>(num_tiles);   // else: dummy tile
-        for (int h = 0; h < n_halves; ++h) {
+        for (int uh = 0; uh < units_per_tile; ++uh) {
+          const int h = nsplit ? static_cast<int>(crank) : uh;          // my 256-column block
           for (int ks = 0; ks < ksteps; ++ks, ++it) {
             const uint32_t stage = it % Cfg::kStages;
             const uint32_t phase = (it / Cfg::kStages) & 1;
@@ -234,19 +251,26 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
             const bool a_copy = tile_ok && ki.is_img;
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);   // free in every CTA of the cluster
             ptx::mbar_arrive_expect_tx(&full_bar[stage], b_bytes + (a_copy ? a_bytes : 0u));
+            uint8_t* a_dst = stage_base + stage * Cfg::kStageBytes;
             if (a_copy) {
               const SegInfo sg = s_seg[ki.seg];
-              ptx::bulk_g2s(stage_base + stage * Cfg::kStageBytes,
-                            sg.img + (static_cast<size_t>(tile) * sg.ksteps + (ki.koff >> 4)) *
-                                         GCB_A_IMAGE_BLOCK,
-                            a_bytes, &full_bar[stage]);
+              const uint8_t* a_src = sg.img + (static_cast<size_t>(tile) * sg.ksteps + (ki.koff >> 4)) *
+                                                  GCB_A_IMAGE_BLOCK;
+              if (nsplit) {
+                // Same tile in both CTAs: each fetches half of the block, multicast to both.
+                const uint32_t a_half = a_bytes / 2;
+                ptx::bulk_g2s_multicast(a_dst + crank * a_half, a_src + crank * a_half, a_half,
+                                        &full_bar[stage], cmask);
+              } else {
+                ptx::bulk_g2s(a_dst, a_src, a_bytes, &full_bar[stage]);
+              }
             }
-            uint8_t* dst = stage_base + stage * Cfg::kStageBytes + Cfg::kAStageBytes;
+            uint8_t* dst = a_dst + Cfg::kAStageBytes;
             const uint8_t* src = wimg + (static_cast<size_t>(ks) * n_halves + h) * b_block;
-            if (csize == 1) {
-              ptx::bulk_g2s(dst, src, b_bytes, &full_bar[stage]);
+            if (csize == 1 || nsplit) {
+              ptx::bulk_g2s(dst, src, b_bytes, &full_bar[stage]);    // my own weight block
             } else {
-              // Each CTA fetches 1/csize of the block and multicasts it to all of them.
+              // Same block in every CTA: each fetches 1/csize and multicasts it to all.
               ptx::bulk_g2s_multicast(dst + crank * slice, src + crank * slice, slice,
                                       &full_bar[stage], cmask);
             }
@@ -260,7 +284,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
       const uint32_t idesc = ptx::make_idesc_bf16(kTileM, kUnitN);
       uint32_t it = 0, u = 0;
       for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles); base += tile_stride) {
-        for (int h = 0; h < n_halves; ++h, ++u) {
+        for (int uh = 0; uh < units_per_tile; ++uh, ++u) {
           const uint32_t buf = u & 1;
           ptx::mbar_wait(&tmem_empty_bar[buf], ((u >> 1) & 1) ^ 1);
           ptx::tc_fence_after_sync();
@@ -484,12 +508,37 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
       if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
     };
 
+    // Sum over the valid columns of one unit: pass A (sum) or pass B (sum of squared
+    // deviations from `centre`).
+    auto unit_moment = [&](uint32_t taddr, int col_base, int ncols, float centre, bool squares) {
+      float acc0 = 0.f, acc1 = 0.f;
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        float v[32];
+        ptx::tmem_ld32(taddr + c0, v);
+        float b[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(&b[4 * q]) =
+              *reinterpret_cast<const float4*>(s_bias + col_base + c0 + 4 * q);
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float x0 = v[j] + b[j] - centre, x1 = v[j + 1] + b[j + 1] - centre;
+          if (c0 + j >= ncols) x0 = 0.f;
+          if (c0 + j + 1 >= ncols) x1 = 0.f;
+          if (squares) { acc0 = fmaf(x0, x0, acc0); acc1 = fmaf(x1, x1, acc1); }
+          else { acc0 += x0; acc1 += x1; }
+        }
+      }
+      return acc0 + acc1;
+    };
+
     uint32_t u = 0;
     for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles); base += tile_stride) {
-      const uint32_t tile = base + crank;
+      const uint32_t tile = base + tile_off;
       const long long row0 = static_cast<long long>(tile) * kTileM + ew * 32;
       if (!kLN) {
-        for (int h = 0; h < n_halves; ++h, ++u) {
+        for (int uh = 0; uh < units_per_tile; ++uh, ++u) {
+          const int h = nsplit ? static_cast<int>(crank) : uh;
           const uint32_t buf = u & 1;
           ptx::mbar_wait(&tmem_full_bar[buf], (u >> 1) & 1);
           ptx::tc_fence_after_sync();
@@ -500,6 +549,33 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
           if (ew == 0 && lane == 0) trace(u, 5);
           release(buf);
         }
+      } else if (nsplit) {
+        // LayerNorm over a row whose two halves live in the two CTAs of the cluster: each
+        // CTA computes (mean, M2) of its 256 columns, hands them to the partner through
+        // distributed shared memory, and both combine them (Chan's parallel update).
+        const uint32_t buf = u & 1, par = (u >> 1) & 1;
+        ptx::mbar_wait(&tmem_full_bar[buf], par);
+        ptx::tc_fence_after_sync();
+        if (ew == 0 && lane == 0) trace(u, 3);
+        const int col_base = static_cast<int>(crank) * kUnitN;
+        const uint32_t taddr = tmem_base + lane_base + buf * kUnitN;
+        const float mean_h = unit_moment(taddr, col_base, kUnitN, 0.f, false) * (1.0f / kUnitN);
+        const float m2_h = unit_moment(taddr, col_base, kUnitN, mean_h, true);
+        const int myrow = ew * 32 + lane;
+        const uint32_t peer = crank ^ 1u;
+        ptx::st_cluster_f32x2(ptx::mapa(ptx::smem_addr(&s_lnx[buf * kTileM + myrow]), peer), mean_h, m2_h);
+        ptx::mbar_arrive_remote(ptx::mapa(ptx::smem_addr(&lnx_bar[buf]), peer));
+        ptx::mbar_wait_cluster(&lnx_bar[buf], par);
+        const float2 other = s_lnx[buf * kTileM + myrow];
+        const float delta = other.x - mean_h;
+        const float mean = 0.5f * (mean_h + other.x);
+        const float var = (m2_h + other.y + delta * delta * (0.5f * kUnitN)) * (1.0f / (2 * kUnitN));
+        const float rstd = rsqrtf(var + 1e-5f);
+        if (ew == 0 && lane == 0) trace(u, 4);
+        finish_unit(taddr, tile, row0, col_base, kUnitN, mean, rstd);
+        if (ew == 0 && lane == 0) trace(u, 5);
+        release(buf);
+        ++u;
       } else {
         // Statistics over all units of the row (overlapping the MMAs of the later ones),
         // then normalise / store unit by unit, releasing each accumulator as soon as done.
@@ -545,8 +621,11 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
       // chunk: 8 lanes read one 128-byte line segment of a gathered row.
       const int cgp = tid_g & 7, rp = tid_g >> 3;
       uint32_t gc = 0;
+      // Columns this CTA finishes: its own 256-wide block when N-split, else all n.
+      const int gcol_lo = nsplit ? static_cast<int>(crank) * kUnitN : 0;
+      const int gcol_hi = nsplit ? gcol_lo + kUnitN : n;
       for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles); base += tile_stride) {
-        const long long trow0 = static_cast<long long>(base + crank) * kTileM;
+        const long long trow0 = static_cast<long long>(base + tile_off) * kTileM;
         const float* p0[8];
         const float* p1[8];
 #pragma unroll
@@ -562,7 +641,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
             }
           }
         }
-        for (int c0 = 0; c0 < n; c0 += 32, ++gc) {
+        for (int c0 = gcol_lo; c0 < gcol_hi; c0 += 32, ++gc) {
           const uint32_t gb = gc & 1;
           if (a_is_img && gb != static_cast<uint32_t>(group)) continue;
           float4 acc[8];
@@ -591,7 +670,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
       // ----- activation (A operand) producer -----
       uint32_t it = 0;
       for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles); base += tile_stride) {
-        const uint32_t tile = base + crank;          // may be past the end: all-zero dummy tile
+        const uint32_t tile = base + tile_off;       // may be past the end: all-zero dummy tile
         // Source row of each of my 4 tile rows, per segment (-1 = out of range).
         long long src[3][4];
 #pragma unroll
@@ -606,7 +685,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
             }
           }
         }
-        for (int h = 0; h < n_halves; ++h) {
+        for (int uh = 0; uh < units_per_tile; ++uh) {
           float4 cur[4];
           bool have_cur = false, cur_img = false;
           uint32_t cur_it = 0;

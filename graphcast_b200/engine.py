@@ -4,7 +4,7 @@ drives the C ABI (`gcb_forward`) for one GraphCast instance on one GPU.
 PyTorch is used for device memory and streams only; all arithmetic of the step
 runs in libgraphcast_b200.so.  HBM layout (fp32 unless noted):
 
-  grid_in    [Ng, c_in_pad]     packed, normalised inputs + 3 structural + zero pad
+  grid_in    image [Ng, c_in_pad]  packed, normalised inputs + 3 structural + zero pad
   grid_lat   [Ng, 512]          latent grid nodes (updated in place vg0->vg1->vg2)
   mesh_lat   [Nm, 512]          latent mesh nodes (updated in place, 1 + 16 times)
   mesh_agg   [Nm, 512]          segment sums
@@ -105,6 +105,9 @@ class Engine:
     self.g2m_snd, self.g2m_rcv = self._dev(s1, torch.int32), self._dev(r1, torch.int32)
     self.g2m_row_ptr = self._dev(rp1, torch.int32)
     self.g2m_feat = self._dev(g.g2m_edge_feats[p1], torch.float32)
+    heavy = np.nonzero(np.diff(rp1) > 256)[0].astype(np.int32)     # pole-side receivers
+    self.g2m_heavy = self._dev(heavy if heavy.size else np.zeros([1], np.int32), torch.int32)
+    m.g2m_heavy, m.n_g2m_heavy = self._ptr(self.g2m_heavy), int(heavy.size)
     self.mesh_snd, self.mesh_rcv = self._dev(s2, torch.int32), self._dev(r2, torch.int32)
     self.mesh_row_ptr = self._dev(rp2, torch.int32)
     self.mesh_feat = self._dev(g.mesh_edge_feats[p2], torch.float32)
@@ -242,7 +245,6 @@ class Engine:
     self.hidden = self._image(max_rows)
     self.edge_a_img = self._image(big_edges)
     self.edge_b = f(big_edges, LATENT)
-    self.grid_in = f(m.num_grid, self.c_in_pad)
     self.grid_in_img = self._image(m.num_grid, self.c_in_pad)
     self.mesh_in_img = self._image(m.num_mesh, self.c_in_pad)
     self.grid_lat, self.grid_lat_img = f(m.num_grid, LATENT), self._image(m.num_grid)
@@ -256,7 +258,7 @@ class Engine:
     _native.check(self._lib.gcb_rows_to_image(self.mesh_in.data_ptr(), self.c_in_pad, 1, m.num_mesh,
                                               self.c_in_pad, self.mesh_in_img.data_ptr(),
                                               self._stream()), "gcb_rows_to_image")
-    for name in ("hidden", "edge_a_img", "edge_b", "grid_in_img", "mesh_in_img", "grid_lat",
+    for name in ("hidden", "edge_a_img", "edge_b", "mesh_in_img", "grid_lat",
                  "grid_lat_img", "mesh_lat", "mesh_lat_img", "mesh_agg", "mesh_agg_img",
                  "mesh_edge", "mesh_edge_img", "mesh_msg", "grid_agg_img"):
       setattr(m, name, self._ptr(getattr(self, name)))
@@ -267,7 +269,7 @@ class Engine:
       m.proj_mesh_a, m.proj_mesh_b = self._ptr(self.proj_mesh_a), self._ptr(self.proj_mesh_b)
 
   def workspace_bytes(self) -> int:
-    ts = [self.hidden, self.edge_a_img, self.edge_b, self.grid_in, self.grid_in_img,
+    ts = [self.hidden, self.edge_a_img, self.edge_b, self.grid_in_img,
           self.mesh_in_img, self.grid_lat, self.grid_lat_img, self.mesh_lat, self.mesh_lat_img,
           self.mesh_agg, self.mesh_agg_img, self.mesh_edge, self.mesh_edge_img, self.mesh_msg,
           self.grid_agg_img, self.grid_out]
@@ -287,22 +289,23 @@ class Engine:
   def pack_inputs(self, planes: torch.Tensor, mean: Optional[torch.Tensor] = None,
                   scale: Optional[torch.Tensor] = None,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """planes [c_in, Ng] (device, fp32, contiguous) -> grid_in [Ng, c_in_pad]."""
+    """planes [c_in, Ng] (device, fp32, contiguous) -> operand image of the packed,
+    normalised grid features [Ng, c_in_pad] (with the 3 structural features)."""
     if planes.shape != (self.c_in, self.num_grid) or planes.dtype != torch.float32 \
         or not planes.is_contiguous() or planes.device != self.device:
       raise ValueError(f"planes must be a contiguous fp32 [{self.c_in}, {self.num_grid}] "
                        f"tensor on {self.device}")
-    out = self.grid_in if out is None else out
-    _native.check(self._lib.gcb_pack_grid_features(
+    out = self.grid_in_img if out is None else out
+    _native.check(self._lib.gcb_pack_grid_image(
         planes.data_ptr(), self.c_in, self.num_grid, self._ptr(mean), self._ptr(scale),
-        self.grid_static.data_ptr(), 3, out.data_ptr(), self.c_in_pad, self._stream()),
-        "gcb_pack_grid_features")
+        self.grid_static.data_ptr(), 3, self.c_in_pad, out.data_ptr(), self._stream()),
+        "gcb_pack_grid_image")
     return out
 
   def step(self, grid_in: Optional[torch.Tensor] = None,
            grid_out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """grid_in [Ng, c_in_pad] -> grid_out [Ng, 256] (n_out valid columns)."""
-    grid_in = self.grid_in if grid_in is None else grid_in
+    """grid_in (operand image of [Ng, c_in_pad]) -> grid_out [Ng, 256] (n_out valid columns)."""
+    grid_in = self.grid_in_img if grid_in is None else grid_in
     grid_out = self.grid_out if grid_out is None else grid_out
     n = C.c_int32(0)
     _native.check(self._lib.gcb_forward(C.byref(self._model), grid_in.data_ptr(),

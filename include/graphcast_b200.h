@@ -155,6 +155,13 @@ int gcb_layer_forward(const gcb_layer_desc* d, void* stream);
 int gcb_segment_sum(const float* msg, int32_t ld_msg, const int32_t* row_ptr, int32_t num_nodes,
                     float* out, int32_t ld_out, int32_t width, void* stream);
 
+/* Same, with the receivers of more than 256 in-edges listed in `heavy` (node ids, host-computed
+ * from row_ptr): those are summed by one thread block each instead of one warp (the mesh
+ * nodes next to the poles receive thousands of grid points).  Deterministic. */
+int gcb_segment_sum_heavy(const float* msg, int32_t ld_msg, const int32_t* row_ptr,
+                          int32_t num_nodes, const int32_t* heavy, int32_t num_heavy, float* out,
+                          int32_t ld_out, int32_t width, void* stream);
+
 /* Channel packing, device side.  planes: [n_ch, n_nodes] (channel-major, i.e. the
  * (batch-sliced) variables stacked in dataset_to_stacked order);  feats:
  * [n_nodes, ld] with columns [0,n_ch) = (planes - mean) / scale (mean/scale per
@@ -167,6 +174,12 @@ int gcb_pack_grid_features(const float* planes, int32_t n_ch, int64_t n_nodes,
                            const float* mean, const float* scale,
                            const float* node_static, int32_t n_static,
                            float* feats, int32_t ld, void* stream);
+
+/* Same packing, delivered directly as the operand image of the [n_nodes, k] feature matrix
+ * (k = padded channel count, multiple of 16, >= n_ch + n_static): what gcb_forward consumes. */
+int gcb_pack_grid_image(const float* planes, int32_t n_ch, int64_t n_nodes, const float* mean,
+                        const float* scale, const float* node_static, int32_t n_static,
+                        int32_t k, void* img, void* stream);
 
 /* Inverse for the outputs: y [n_nodes, ld_y] -> planes_out [n_out, n_nodes] with
  *   planes_out[c] = y[:, c] * scale[c] + offset[c] + (add_plane_index[c] >= 0 ?
@@ -215,6 +228,7 @@ typedef struct {
   /* static graph */
   const int32_t* g2m_snd; const int32_t* g2m_rcv; const int32_t* g2m_row_ptr;
   const float*   g2m_feat;   /* [e_g2m, 4] */
+  const int32_t* g2m_heavy; int32_t n_g2m_heavy;   /* receivers with > 256 in-edges */
   const int32_t* mesh_snd; const int32_t* mesh_rcv; const int32_t* mesh_row_ptr;
   const float*   mesh_feat;  /* [e_mesh, 4] */
   const int32_t* m2g_snd; const int32_t* m2g_rcv;
@@ -243,7 +257,6 @@ typedef struct {
   void* hidden;         /* image [max_rows, 512]: hidden activations of the current MLP */
   void* edge_a_img;     /* image [max(e_g2m,e_m2g), 512]: embedded bipartite edge latents */
   float* edge_b;        /* [max(e_g2m,e_m2g), 512] bipartite messages */
-  void* grid_in_img;    /* image [num_grid, c_in_pad] */
   const void* mesh_in_img;  /* image [num_mesh, c_in_pad] of mesh_in (static) */
   float* grid_lat;  void* grid_lat_img;    /* [num_grid, 512] latent grid nodes */
   float* mesh_lat;  void* mesh_lat_img;    /* [num_mesh, 512] latent mesh nodes */
@@ -254,14 +267,14 @@ typedef struct {
 } gcb_model;
 
 /* One 6 h step for one batch element:
- *   grid_in  [num_grid, c_in_pad]  (from gcb_pack_grid_features)
+ *   grid_in_img  operand image of [num_grid, c_in_pad]  (from gcb_pack_grid_image)
  *   grid_out [num_grid, 256]       (columns [0, n_out) valid)
  * Replaces GraphCast.__call__'s _run_grid2mesh_gnn / _run_mesh_gnn /
  * _run_mesh2grid_gnn (weathernext1_graph/graphcast.py:309-323, 550-678) and the
  * DeepTypedGraphNet / InteractionNetwork machinery under them
  * (utils/legacy/deep_typed_graph_net.py:180-401, utils/typed_graph_net.py:272-546).
  * `launches` (host pointer, may be NULL) receives the number of kernels launched. */
-int gcb_forward(const gcb_model* m, const float* grid_in, float* grid_out, void* stream,
+int gcb_forward(const gcb_model* m, const void* grid_in_img, float* grid_out, void* stream,
                 int32_t* launches);
 
 /* Per-launch profiling.  Between gcb_profile_begin() and gcb_profile_end() every

@@ -31,6 +31,18 @@ def test_segment_sum_skewed_degrees_and_empty_rows():
   lib.gcb_segment_sum(msg.data_ptr(), 512, rp.data_ptr(), 3000, out2.data_ptr(), 512, 512,
                       torch.cuda.current_stream().cuda_stream)
   assert torch.equal(out, out2)
+  # heavy-receiver path: nodes with > 256 in-edges get one block each; same result, deterministic
+  heavy = torch.as_tensor(np.nonzero(deg > 256)[0].astype(np.int32)).to(dev)
+  out3 = torch.full((3000, 512), float("nan"), device=dev)
+  _native.check(lib.gcb_segment_sum_heavy(msg.data_ptr(), 512, rp.data_ptr(), 3000, heavy.data_ptr(),
+                                          heavy.numel(), out3.data_ptr(), 512, 512,
+                                          torch.cuda.current_stream().cuda_stream), "segsum_heavy")
+  torch.testing.assert_close(out3.double(), want, rtol=1e-5, atol=2e-3)
+  assert torch.equal(out3[5], out[5]) and torch.equal(out3[100], out[100])
+  out4 = torch.empty_like(out3)
+  lib.gcb_segment_sum_heavy(msg.data_ptr(), 512, rp.data_ptr(), 3000, heavy.data_ptr(), heavy.numel(),
+                            out4.data_ptr(), 512, 512, torch.cuda.current_stream().cuda_stream)
+  assert torch.equal(out3, out4)
 
 
 def test_pack_and_unpack_are_exact_transposes_with_affine():
@@ -52,6 +64,18 @@ def test_pack_and_unpack_are_exact_transposes_with_affine():
   _native.check(lib.gcb_pack_grid_features(planes.data_ptr(), n_ch, n_nodes, None, None,
                                            static.data_ptr(), 3, feats.data_ptr(), ld, st), "pack")
   assert torch.equal(feats[:, :n_ch], planes.t())
+
+  # direct operand-image packing == image of the fp32 packing
+  _native.check(lib.gcb_pack_grid_features(planes.data_ptr(), n_ch, n_nodes, mean.data_ptr(),
+                                           scale.data_ptr(), static.data_ptr(), 3,
+                                           feats.data_ptr(), ld, st), "pack")
+  img_a = torch.zeros(lib.gcb_a_image_bytes(n_nodes, ld), dtype=torch.uint8, device=dev)
+  img_b = torch.zeros_like(img_a)
+  _native.check(lib.gcb_pack_grid_image(planes.data_ptr(), n_ch, n_nodes, mean.data_ptr(),
+                                        scale.data_ptr(), static.data_ptr(), 3, ld,
+                                        img_a.data_ptr(), st), "pack_image")
+  _native.check(lib.gcb_rows_to_image(feats.data_ptr(), ld, 1, n_nodes, ld, img_b.data_ptr(), st), "to_image")
+  assert torch.equal(img_a, img_b)
 
   y = torch.randn(n_nodes, 256, device=dev)
   oscale, ooff = torch.rand(n_out, device=dev) + 0.5, torch.randn(n_out, device=dev)

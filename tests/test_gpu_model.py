@@ -32,7 +32,7 @@ def test_step_matches_oracle(prec, tol, pregather):
   assert _rel(y, ref) <= tol
   mlp_layers = 2 * (6 + 1 + 2 * 3 + 4)
   projections = 2 * (1 + 3 + 1) if pregather else 0       # two per edge MLP (g2m, 3 mesh steps, m2g)
-  to_image = 1 + 1 + 3 + 1              # grid_in, agg1, 3 x mesh agg, summed m2g messages
+  to_image = 1 + 3 + 1                  # agg1, 3 x mesh agg, summed m2g messages
   assert eng.launches_per_step == mlp_layers + projections + (1 + 3) + to_image   # + segment sums
 
 
