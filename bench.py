@@ -316,6 +316,9 @@ def run_b200(args):
   peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
   peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PF"
   products = {"bf16x3": 3, "bf16": 1, "fp32_simt": 1}[args.precision]
+  # MACs the kernel really issues (the split edge layers execute fewer than the reference
+  # dataflow the algorithmic figure is defined on), times the products per MAC.
+  executed_tflops = (tc[1] / args.steps) * products / (tc_ms_per_step * 1e-3) / 1e12
   roofline = {
       "kernel": "gcb::mlp_layer_tc_kernel", "bound": "tensor",
       "achieved": achieved_tflops, "peak": peak_tf, "unit": "TFLOP/s",
@@ -324,8 +327,9 @@ def run_b200(args):
       "kernel_share_of_step": tc_ms_per_step / (elapsed_ms / args.steps),
       "algorithmic_tflop_per_step": alg_flops / 1e12,
       "tensor_products_per_mac": products,
-      "executed_tensor_tflops": achieved_tflops * products,
-      "tensor_pipe_frac": achieved_tflops * products / peak_tf,
+      "executed_tflop_per_step": tc[1] / args.steps * products / 1e12,
+      "executed_tensor_tflops": executed_tflops,
+      "tensor_pipe_frac": executed_tflops / peak_tf,
       "other_kernels_ms_per_step": {k: v[0] / args.steps for k, v in agg.items() if k != "mlp_layer_tc"},
       "hbm": {k: {"GB_per_step": v[2] / args.steps / 1e9,
                   "GBps": (v[2] / 1e9) / (v[0] * 1e-3) if v[0] > 0 else None}
@@ -333,23 +337,34 @@ def run_b200(args):
   }
 
   # ---------------- end-to-end through the public API ---------------------------
-  host_out = {name: torch.empty(v.shape, dtype=torch.float32, pin_memory=True)
-              for name, v in pred.data_vars.items()}
+  # Serving loop: every step uploads its inputs from pinned host memory (GraphCast.__call__
+  # stages them on its own copy stream, double buffered) and downloads its predictions to
+  # pinned host memory on a second copy stream; the host only synchronises at the end, so
+  # the transfers of neighbouring steps overlap the kernels.  All K uploads, K steps and K
+  # downloads are inside the timed region.
+  host_out = [{name: torch.empty(v.shape, dtype=torch.float32, pin_memory=True)
+               for name, v in pred.data_vars.items()} for _ in range(2)]
+  d2h_stream = torch.cuda.Stream(device=dev)
+  compute = torch.cuda.current_stream(dev)
 
-  def e2e_step():
+  def e2e_step(i):
     p = model(inputs, template, forcings)           # H2D of every input inside
-    for name, v in p.data_vars.items():
-      host_out[name].copy_(v.data, non_blocking=True)   # D2H of the predictions
-    torch.cuda.current_stream().synchronize()
+    done = torch.cuda.Event()
+    done.record(compute)
+    with torch.cuda.stream(d2h_stream):
+      d2h_stream.wait_event(done)
+      for name, v in p.data_vars.items():
+        v.data.record_stream(d2h_stream)
+        host_out[i % 2][name].copy_(v.data, non_blocking=True)   # D2H of the predictions
 
   e2e_steps = max(2, min(args.steps, args.e2e_steps))
-  e2e_step()
+  e2e_step(0)
   torch.cuda.synchronize()
   if world > 1:
     dist.barrier()
   t0 = time.perf_counter()
-  for _ in range(e2e_steps):
-    e2e_step()
+  for i in range(e2e_steps):
+    e2e_step(i)
   torch.cuda.synchronize()
   e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
   t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
@@ -406,7 +421,7 @@ def main():
   ap.add_argument("--cpu-sample", dest="cpu_sample", choices=sorted(WORKLOADS),
                   default="sample_2deg_13lvl",
                   help="bounded CPU sample (a few seconds per step), scaled by algorithmic FLOPs")
-  ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=5)
+  ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=10)
   ap.add_argument("--skip-cpu-baseline", action="store_true")
   ap.add_argument("--cluster", type=int, default=0, help="CTAs per cluster (0 = library default)")
   ap.add_argument("--dump-launches", default="", help="write per-launch (kind, ms, GFLOP, GB) of the last timed step to this file")

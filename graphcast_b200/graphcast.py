@@ -138,6 +138,13 @@ class GraphCast(Predictor):
     self._engine: Optional[engine_lib.Engine] = None
     self._planes_in: Optional[torch.Tensor] = None
     self._planes_out: Optional[torch.Tensor] = None
+    # Host->device staging: two input-plane buffers filled on a dedicated copy stream, so
+    # the H2D transfer of call k+1 overlaps the kernels of call k when the caller does not
+    # synchronise in between (serving loop / ensemble members).
+    self._h2d_stream: Optional[torch.cuda.Stream] = None
+    self._planes_bufs: List[Optional[torch.Tensor]] = [None, None]
+    self._buf_free: List[Optional[torch.cuda.Event]] = [None, None]
+    self._call_index = 0
 
   # -- parameters ------------------------------------------------------------------
   def set_params(self, params: Mapping[str, Mapping[str, np.ndarray]]) -> None:
@@ -199,22 +206,44 @@ class GraphCast(Predictor):
 
     # xarray -> channel-major planes [B, C, lat*lon] on the device
     # (reference _inputs_to_grid_node_features :680-699; dataset_to_stacked order).
-    if self._planes_in is None or self._planes_in.shape != (batch, c_in, eng.num_grid):
-      self._planes_in = torch.empty([batch, c_in, eng.num_grid], dtype=torch.float32,
-                                    device=eng.device)
-      self._planes_out = torch.empty([batch, eng.n_out, eng.num_grid], dtype=torch.float32,
-                                     device=eng.device)
-    planes_in = self._planes_in
+    buf = self._call_index % 2
+    self._call_index += 1
+    if self._planes_bufs[buf] is None or self._planes_bufs[buf].shape != (batch, c_in, eng.num_grid):
+      self._planes_bufs[buf] = torch.empty([batch, c_in, eng.num_grid], dtype=torch.float32,
+                                           device=eng.device)
+      self._buf_free[buf] = None
+    planes_in = self._planes_bufs[buf]
+    self._planes_in = planes_in
+    sources = []
     for ds, slabs in ((inputs, in_slabs), (forcings, f_slabs)):
       for s in slabs:
         src = model_utils.variable_to_planes(ds.data_vars[s.name], sizes)
         if not isinstance(src, torch.Tensor):
           src = torch.from_numpy(np.ascontiguousarray(src, dtype=np.float32))
+        sources.append((s, src))
+    compute = torch.cuda.current_stream(eng.device)
+    all_host = all(src.device.type == "cpu" for _, src in sources)
+    if all_host:
+      if self._h2d_stream is None:
+        self._h2d_stream = torch.cuda.Stream(device=eng.device)
+      copy_stream = self._h2d_stream
+      if self._buf_free[buf] is not None:
+        copy_stream.wait_event(self._buf_free[buf])      # kernels of call k-2 are done with it
+    else:
+      copy_stream = compute                              # device-resident inputs: stay in order
+    with torch.cuda.stream(copy_stream):
+      for s, src in sources:
         dst = planes_in[:, s.start:s.start + s.count].view(batch, s.count, n_lat, n_lon)
         dst.copy_(src, non_blocking=True)
+      if all_host:
+        ready = torch.cuda.Event()
+        ready.record(copy_stream)
+    if all_host:
+      compute.wait_event(ready)
 
     # Predictions are produced into fresh planes each call (they are handed out).
-    planes_out = torch.empty_like(self._planes_out)
+    planes_out = torch.empty([batch, eng.n_out, eng.num_grid], dtype=torch.float32,
+                             device=eng.device)
     for b in range(batch):
       if norm is None:
         eng.pack_inputs(planes_in[b])
@@ -225,6 +254,9 @@ class GraphCast(Predictor):
         eng.step()
         eng.unpack_outputs(planes_out[b], scale=norm.out_scale, offset=norm.out_offset,
                            add_planes=planes_in[b], add_plane_index=norm.add_plane_index)
+    free = torch.cuda.Event()
+    free.record(compute)
+    self._buf_free[buf] = free
 
     # planes -> Dataset shaped like the template
     # (reference _grid_node_outputs_to_prediction :701-723, stacked_to_dataset).
