@@ -227,6 +227,8 @@ def run_b200(args):
   lib = _native.lib()
   if args.cluster:
     _native.check(lib.gcb_set_cluster_size(args.cluster), "gcb_set_cluster_size")
+  if os.environ.get("GCB_DEBUG_FLAGS"):   # kernel experiment switches (gcb_debug_flags); not for results
+    _native.check(lib.gcb_debug_flags(int(os.environ["GCB_DEBUG_FLAGS"])), "gcb_debug_flags")
 
   res, mesh, task_name = WORKLOADS[args.workload]
   task = getattr(graphcast, task_name)

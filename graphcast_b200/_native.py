@@ -103,6 +103,7 @@ EXPORTS = {
     "gcb_forward": (C.c_int, [C.POINTER(Model), _fp, _fp, _fp, C.POINTER(C.c_int32)]),
     "gcb_set_cluster_size": (C.c_int, [C.c_int32]),
     "gcb_debug_trace": (C.c_int, [_fp]),
+    "gcb_debug_flags": (C.c_int, [C.c_int]),
     "gcb_profile_begin": (C.c_int, []),
     "gcb_profile_end": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.POINTER(C.c_int32)]),
     "gcb_selftest_layer": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32,

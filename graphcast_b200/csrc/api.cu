@@ -156,7 +156,7 @@ int g_cluster_size = 2;   // CTAs per cluster sharing the weight stream (1, 2 or
 
 template <bool kSplit, bool kSwish, bool kLN>
 int launch_tc_variant(const gcb_layer_desc& d, cudaStream_t stream) {
-  using Cfg = gcb::TcConfig<kSplit>;
+  using Cfg = gcb::TcConfig<kSplit, kLN>;
   auto kernel = gcb::mlp_layer_tc_kernel<kSplit, kSwish, kLN>;
   static bool attr_set[64] = {false};
   static int max_clusters[64][5] = {{0}};
@@ -642,6 +642,11 @@ int gcb_set_cluster_size(int32_t ctas) {
 int gcb_debug_trace(long long* device_buffer) {
   // device_buffer: [kTraceTiles * kTraceEvents] int64 on the device, or NULL to disable.
   GCB_CUDA(cudaMemcpyToSymbol(gcb::g_trace, &device_buffer, sizeof(device_buffer)));
+  return GCB_OK;
+}
+
+int gcb_debug_flags(int flags) {
+  GCB_CUDA(cudaMemcpyToSymbol(gcb::g_dbg_flags, &flags, sizeof(flags)));
   return GCB_OK;
 }
 

@@ -65,15 +65,27 @@ constexpr int kMaxKSteps = 128;                   // K <= 2048
 constexpr int kTmemCols = 512;
 static_assert(2 * kAPartBytes == GCB_A_IMAGE_BLOCK, "A image block must match the stage layout");
 
-template <bool kSplit>
+// Shared-memory budget: everything the variant does not need goes to pipeline stages -
+// the operand ring is latency-bound (tools/pipe_rate.cu: 6 stages 411, 8 stages 389 cycles
+// per K-step for a 384-cycle bf16x3 K-step).  LayerNorm variants never stage gathered
+// addends (only the 2 KB statistics exchange aliases that region); the others carry no
+// LayerNorm scale / offset.
+constexpr int kSmemLimit = 227 * 1024;            // opt-in dynamic shared memory per CTA
+constexpr int kTailBytes = 1024;                  // barriers, TMEM slot, segment tables
+constexpr int kLnxBytes = 2 * kTileM * 8;         // [2][128] (mean, M2) pairs
+
+template <bool kSplit, bool kLN>
 struct TcConfig {
-  static constexpr int kStages = kSplit ? 6 : 10;
   static constexpr int kAStageBytes = kSplit ? 2 * kAPartBytes : kAPartBytes;
   static constexpr int kBStageBytes = kSplit ? 2 * kBPartBytes : kBPartBytes;
   static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
-  static constexpr int kParamBytes = 3 * kMaxN * 4;  // bias, ln scale, ln offset
-  static constexpr int kSmemBytes =
-      kStages * kStageBytes + kParamBytes + kEpiStageBytes + kGBytes + 1024;
+  static constexpr int kParamBytes = (kLN ? 3 : 1) * kMaxN * 4;   // bias (, ln scale, ln offset)
+  static constexpr int kGRegionBytes = kLN ? kLnxBytes : kGBytes;
+  static constexpr int kFixedBytes = kParamBytes + kEpiStageBytes + kGRegionBytes + kTailBytes;
+  static constexpr int kFit = (kSmemLimit - kFixedBytes) / kStageBytes;
+  static constexpr int kStages = kFit < 12 ? kFit : 12;           // tail holds 2*12+10 barriers
+  static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
+  static_assert(kStages >= 4, "operand ring too shallow");
 };
 
 __device__ __forceinline__ float swish_f(float x) {
@@ -85,12 +97,20 @@ __device__ __forceinline__ float swish_f(float x) {
 // Optional timeline trace (debug): when non-null, CTA 0 records clock64() at a few
 // points of each of its first kTraceTiles units; see gcb_debug_trace in api.cu.
 constexpr int kTraceTiles = 64;
-constexpr int kTraceEvents = 8;
+constexpr int kTraceEvents = 16;
 __device__ long long* g_trace = nullptr;
+// Debug-only experiment switches (gcb_debug_flags); 0 in production.
+__device__ int g_dbg_flags = 0;
 
 __device__ __forceinline__ void trace(uint32_t unit, int ev) {
   if (g_trace != nullptr && blockIdx.x == 0 && unit < kTraceTiles)
     g_trace[unit * kTraceEvents + ev] = clock64();
+}
+__device__ __forceinline__ bool tracing(uint32_t unit) {
+  return g_trace != nullptr && blockIdx.x == 0 && unit < kTraceTiles;
+}
+__device__ __forceinline__ void trace_val(uint32_t unit, int ev, long long v) {
+  if (tracing(unit)) g_trace[unit * kTraceEvents + ev] = v;
 }
 
 struct KStepInfo {
@@ -118,15 +138,15 @@ struct PreAddInfo {
 template <bool kSplit, bool kSwish, bool kLN>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
-  using Cfg = TcConfig<kSplit>;
+  using Cfg = TcConfig<kSplit, kLN>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* stage_base = smem;
   float* s_bias = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  float* s_scale = s_bias + kMaxN;
-  float* s_offset = s_scale + kMaxN;
-  float* s_epi = s_offset + kMaxN;                                  // [4][32][36]
-  float* s_g = s_epi + 4 * 32 * kEpiRowFloats;                      // [2][128][36]
-  uint8_t* tail = reinterpret_cast<uint8_t*>(s_g + 2 * kGBufFloats);
+  float* s_scale = s_bias + kMaxN;                                  // LayerNorm variants only
+  float* s_offset = s_scale + kMaxN;                                // LayerNorm variants only
+  float* s_epi = s_bias + Cfg::kParamBytes / 4;                     // [4][32][36]
+  float* s_g = s_epi + 4 * 32 * kEpiRowFloats;                      // [2][128][36] (not kLN)
+  uint8_t* tail = reinterpret_cast<uint8_t*>(s_g) + Cfg::kGRegionBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);          // [kStages]
   uint64_t* empty_bar = full_bar + Cfg::kStages;                   // [kStages]
   uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;              // [2]
@@ -155,13 +175,14 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
     ksteps += d.seg[s].k / kKStep;
     a_is_img = a_is_img && (d.seg[s].img != nullptr);
   }
-  uint8_t* const out_img = static_cast<uint8_t*>(d.out_img);
+  const int dbg = g_dbg_flags;
+  uint8_t* const out_img = (dbg & 2) ? nullptr : static_cast<uint8_t*>(d.out_img);
   // Descriptor fields used inside hot loops, hoisted into registers once.
   const long long rows_total = d.rows;
   const int nseg = d.nseg;
   const int n_pre = d.n_pre_add;               // gathered pre-activation addends (0..2)
-  float* const out_ptr = d.out;
-  float* const outy_ptr = d.out_y;
+  float* const out_ptr = (dbg & 2) ? nullptr : d.out;
+  float* const outy_ptr = (dbg & 2) ? nullptr : d.out_y;
   const float* const res_ptr = d.residual;
   const long long ld_out = d.ld_out, ld_outy = d.ld_out_y, ld_res = d.ld_res;
   // Cluster schedule: the CTAs of a cluster walk the K-steps of `csize` consecutive
@@ -175,12 +196,17 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
   const uint32_t tile_off = nsplit ? 0u : crank;             // my tile = base + tile_off
   const int units_per_tile = nsplit ? 1 : n_halves;          // units this CTA runs per tile
   const uint16_t cmask = static_cast<uint16_t>((1u << csize) - 1u);
+  // (experiment, debug flag 4) N-split pair without A multicast: each CTA streams the whole
+  // block itself and recycles its stages on its own MMAs only.
+  const bool decouple = nsplit && (dbg & 4);
 
   // ---- one-time setup ---------------------------------------------------------
   for (int i = threadIdx.x; i < n; i += kThreads) {
     s_bias[i] = d.bias[i];
-    s_scale[i] = kLN ? d.ln_scale[i] : 1.0f;
-    s_offset[i] = kLN ? d.ln_offset[i] : 0.0f;
+    if (kLN) {
+      s_scale[i] = d.ln_scale[i];
+      s_offset[i] = d.ln_offset[i];
+    }
   }
   if (threadIdx.x == 0) {
     int ks = 0;
@@ -208,7 +234,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       // 1 TMA lane (+ 4 activation-producer warps unless A comes from images only)
       ptx::mbar_init(&full_bar[s], a_is_img ? 1 : 5);
-      ptx::mbar_init(&empty_bar[s], csize);  // tcgen05.commit of every CTA in the cluster
+      ptx::mbar_init(&empty_bar[s], decouple ? 1 : csize);  // tcgen05.commit of every CTA in the cluster
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tmem_full_bar[b], 1);
@@ -231,88 +257,122 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
 
   // ---- roles ------------------------------------------------------------------
   if (warp == 0) {
-    // ===== TMA lane =====
-    if (lane == 0) {
-      const uint32_t b_bytes = Cfg::kBStageBytes;                 // hi (| lo) of a 256-row block
-      const size_t b_block = 2 * kBPartBytes;                     // image always holds hi|lo
-      const uint8_t* wimg = static_cast<const uint8_t*>(d.w_packed);
-      const uint32_t slice = b_bytes / csize;
-      const uint32_t a_bytes = Cfg::kAStageBytes;                 // hi (| lo) block of one K-step
-      uint32_t it = 0;
-      for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles); base += tile_stride) {
-        const uint32_t tile = base + tile_off;
-        const bool tile_ok = tile < static_cast<uint32_t>(num_tiles);   // else: dummy tile
-        for (int uh = 0; uh < units_per_tile; ++uh) {
-          const int h = nsplit ? static_cast<int>(crank) : uh;          // my 256-column block
-          for (int ks = 0; ks < ksteps; ++ks, ++it) {
-            const uint32_t stage = it % Cfg::kStages;
-            const uint32_t phase = (it / Cfg::kStages) & 1;
-            const KStepInfo ki = ks_info[ks];
-            const bool a_copy = tile_ok && ki.is_img;
+    // ===== TMA warp =====
+    // Converged warp, every lane polls, ONE elected lane issues (see the MMA warp).  The
+    // loop body is kept minimal - running pointers, ring counters, one SegInfo read per
+    // segment: the issuing warp shares its scheduler with an epilogue warp, and a body of
+    // ~500 cycles per K-step (table lookups + 64-bit address math + waterfall loops) made
+    // this warp, not HBM or the tensor pipe, the limiter of the whole kernel.
+    const uint32_t b_bytes = Cfg::kBStageBytes;                 // hi (| lo) of a 256-row block
+    const size_t b_block = 2 * kBPartBytes;                     // image always holds hi|lo
+    const size_t b_stride = static_cast<size_t>(n_halves) * b_block;   // next K-step, same half
+    const uint32_t slice = b_bytes / csize;
+    const uint32_t a_bytes = Cfg::kAStageBytes;                 // hi (| lo) block of one K-step
+    const uint32_t a_half = a_bytes / 2;
+    const bool b_own = (csize == 1) || nsplit;                  // my own weight block, no multicast
+    const uint8_t* wimg = static_cast<const uint8_t*>(d.w_packed);
+    uint32_t stage = 0, phase = 0, tu = 0;
+    for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles); base += tile_stride) {
+      const uint32_t tile = base + tile_off;
+      const bool tile_ok = tile < static_cast<uint32_t>(num_tiles);   // else: dummy tile
+      for (int uh = 0; uh < units_per_tile; ++uh, ++tu) {
+        const int h = nsplit ? static_cast<int>(crank) : uh;          // my 256-column block
+        const uint8_t* b_ptr = wimg + static_cast<size_t>(h) * b_block + (b_own ? 0u : crank * slice);
+        const bool tr = tracing(tu);
+        long long blocked = 0;
+        for (int s = 0; s < nseg; ++s) {
+          const SegInfo sg = s_seg[s];
+          const bool a_copy = tile_ok && sg.img != nullptr;
+          // Same tile in both CTAs of an N-split pair: each fetches half of every block and
+          // multicasts it to both.
+          const uint8_t* a_ptr = sg.img + static_cast<size_t>(tile) * sg.ksteps * GCB_A_IMAGE_BLOCK +
+                                 (nsplit && !decouple ? crank * a_half : 0u);
+          const uint32_t tx = b_bytes + (a_copy ? a_bytes : 0u);
+          // (experiment, debug flag 16) L2 prefetch of the same block of my next tile
+          const bool pf_next = (dbg & 16) && uh == units_per_tile - 1 &&
+                               tile + tile_stride < static_cast<uint32_t>(num_tiles);
+          const size_t pf_off = static_cast<size_t>(tile_stride) * sg.ksteps * GCB_A_IMAGE_BLOCK;
+          for (int k = 0; k < sg.ksteps; ++k) {
+            const long long w0 = tr ? clock64() : 0;
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);   // free in every CTA of the cluster
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], b_bytes + (a_copy ? a_bytes : 0u));
+            if (tr) blocked += clock64() - w0;
             uint8_t* a_dst = stage_base + stage * Cfg::kStageBytes;
-            if (a_copy) {
-              const SegInfo sg = s_seg[ki.seg];
-              const uint8_t* a_src = sg.img + (static_cast<size_t>(tile) * sg.ksteps + (ki.koff >> 4)) *
-                                                  GCB_A_IMAGE_BLOCK;
-              if (nsplit) {
-                // Same tile in both CTAs: each fetches half of the block, multicast to both.
-                const uint32_t a_half = a_bytes / 2;
-                ptx::bulk_g2s_multicast(a_dst + crank * a_half, a_src + crank * a_half, a_half,
-                                        &full_bar[stage], cmask);
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(&full_bar[stage], tx);
+              if (pf_next && a_copy) ptx::bulk_prefetch_l2(a_ptr + pf_off, nsplit ? a_half : a_bytes);
+              if (a_copy) {
+                if (nsplit && !decouple) ptx::bulk_g2s_multicast(a_dst + crank * a_half, a_ptr, a_half, &full_bar[stage], cmask);
+                else ptx::bulk_g2s(a_dst, a_ptr, a_bytes, &full_bar[stage]);
+              }
+              if (b_own) {
+                ptx::bulk_g2s(a_dst + Cfg::kAStageBytes, b_ptr, b_bytes, &full_bar[stage]);
               } else {
-                ptx::bulk_g2s(a_dst, a_src, a_bytes, &full_bar[stage]);
+                // Same block in every CTA: each fetches 1/csize and multicasts it to all.
+                ptx::bulk_g2s_multicast(a_dst + Cfg::kAStageBytes + crank * slice, b_ptr, slice,
+                                        &full_bar[stage], cmask);
               }
             }
-            uint8_t* dst = a_dst + Cfg::kAStageBytes;
-            const uint8_t* src = wimg + (static_cast<size_t>(ks) * n_halves + h) * b_block;
-            if (csize == 1 || nsplit) {
-              ptx::bulk_g2s(dst, src, b_bytes, &full_bar[stage]);    // my own weight block
-            } else {
-              // Same block in every CTA: each fetches 1/csize and multicasts it to all.
-              ptx::bulk_g2s_multicast(dst + crank * slice, src + crank * slice, slice,
-                                      &full_bar[stage], cmask);
-            }
+            __syncwarp();
+            a_ptr += GCB_A_IMAGE_BLOCK;
+            b_ptr += b_stride;
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           }
         }
+        if (lane == 0) trace_val(tu, 7, blocked);
       }
     }
   } else if (warp == 1) {
-    // ===== MMA lane =====
-    if (lane == 0) {
+    // ===== MMA warp =====
+    // The whole warp runs the loop on warp-uniform values and ONE elected lane issues the
+    // tcgen05 instructions.  Under `if (lane == 0)` every operand is divergent and the
+    // compiler wraps each UTCHMMA / UTCBAR in a vector->uniform "waterfall" loop, which
+    // made the issuing thread, not the tensor pipe, the limiter (tools/pipe_rate.cu: 432 vs
+    // 389 cycles per K-step).  All lanes poll: a single poller with 31 lanes parked at the
+    // warp barrier is 2x slower (same benchmark, style 2).
+    {
       const uint32_t idesc = ptx::make_idesc_bf16(kTileM, kUnitN);
-      uint32_t it = 0, u = 0;
+      uint32_t stage = 0, phase = 0, u = 0;
       for (uint32_t base = tile_first; base < static_cast<uint32_t>(num_tiles); base += tile_stride) {
         for (int uh = 0; uh < units_per_tile; ++uh, ++u) {
           const uint32_t buf = u & 1;
           ptx::mbar_wait(&tmem_empty_bar[buf], ((u >> 1) & 1) ^ 1);
           ptx::tc_fence_after_sync();
-          trace(u, 0);
+          if (lane == 0) trace(u, 0);
           const uint32_t dcol = tmem_base + buf * kUnitN;
-          for (int ks = 0; ks < ksteps; ++ks, ++it) {
-            const uint32_t stage = it % Cfg::kStages;
-            const uint32_t phase = (it / Cfg::kStages) & 1;
+          long long starved = 0;
+          const bool tr = tracing(u);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const long long w0 = tr ? clock64() : 0;
             ptx::mbar_wait(&full_bar[stage], phase);
+            if (tr) starved += clock64() - w0;
             ptx::tc_fence_after_sync();
-            if (ks == 0) trace(u, 1);
+            if (ks == 0 && lane == 0) trace(u, 1);
             const uint32_t sa = ptx::smem_addr(stage_base + stage * Cfg::kStageBytes);
             const uint32_t sb = sa + Cfg::kAStageBytes;
             const uint64_t a_hi = ptx::make_smem_desc(sa, kALbo, 128);
             const uint64_t b_hi = ptx::make_smem_desc(sb, kBLbo, 128);
-            ptx::mma_bf16_ss(dcol, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
-            if (kSplit) {
-              const uint64_t a_lo = ptx::make_smem_desc(sa + kAPartBytes, kALbo, 128);
-              const uint64_t b_lo = ptx::make_smem_desc(sb + kBPartBytes, kBLbo, 128);
-              ptx::mma_bf16_ss(dcol, a_hi, b_lo, idesc, 1u);
-              ptx::mma_bf16_ss(dcol, a_lo, b_hi, idesc, 1u);
+            if (ptx::elect_one()) {
+              ptx::mma_bf16_ss(dcol, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
+              if (kSplit) {
+                // descriptors differ only in the 16-byte-unit start address field
+                const uint64_t a_lo = a_hi + (kAPartBytes >> 4);
+                const uint64_t b_lo = b_hi + (kBPartBytes >> 4);
+                ptx::mma_bf16_ss(dcol, a_hi, b_lo, idesc, 1u);
+                ptx::mma_bf16_ss(dcol, a_lo, b_hi, idesc, 1u);
+              }
+              // stage reusable (cluster-wide) once these MMAs retire
+              if (csize == 1 || decouple) ptx::mma_commit(&empty_bar[stage]);
+              else ptx::mma_commit_multicast(&empty_bar[stage], cmask);
             }
-            // stage reusable (cluster-wide) once these MMAs retire
-            if (csize == 1) ptx::mma_commit(&empty_bar[stage]);
-            else ptx::mma_commit_multicast(&empty_bar[stage], cmask);
+            __syncwarp();
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           }
-          ptx::mma_commit(&tmem_full_bar[buf]);          // accumulator complete
-          trace(u, 2);
+          if (ptx::elect_one()) ptx::mma_commit(&tmem_full_bar[buf]);          // accumulator complete
+          __syncwarp();
+          if (lane == 0) {
+            trace(u, 2);
+            trace_val(u, 6, starved);
+          }
         }
       }
     }
@@ -508,11 +568,11 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
       if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
     };
 
-    // Sum over the valid columns of one unit: pass A (sum) or pass B (sum of squared
-    // deviations from `centre`).
-    auto unit_moment = [&](uint32_t taddr, int col_base, int ncols, float centre, bool squares) {
-      float acc0 = 0.f, acc1 = 0.f;
-      for (int c0 = 0; c0 < ncols; c0 += 32) {
+    // One pass over a full 256-column unit: shifted sums  s1 = sum(x - shift),
+    // s2 = sum((x - shift)^2)  with shift = the row's first value of this unit.
+    auto unit_shifted_sums = [&](uint32_t taddr, int col_base, float& shift, float& s1, float& s2) {
+      float p1 = 0.f, p2 = 0.f, q1 = 0.f, q2 = 0.f;     // two chains for ILP
+      for (int c0 = 0; c0 < kUnitN; c0 += 32) {
         float v[32];
         ptx::tmem_ld32(taddr + c0, v);
         float b[32];
@@ -520,16 +580,16 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
         for (int q = 0; q < 8; ++q)
           *reinterpret_cast<float4*>(&b[4 * q]) =
               *reinterpret_cast<const float4*>(s_bias + col_base + c0 + 4 * q);
+        if (c0 == 0) shift = v[0] + b[0];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          float x0 = v[j] + b[j] - centre, x1 = v[j + 1] + b[j + 1] - centre;
-          if (c0 + j >= ncols) x0 = 0.f;
-          if (c0 + j + 1 >= ncols) x1 = 0.f;
-          if (squares) { acc0 = fmaf(x0, x0, acc0); acc1 = fmaf(x1, x1, acc1); }
-          else { acc0 += x0; acc1 += x1; }
+          const float x0 = v[j] + b[j] - shift, x1 = v[j + 1] + b[j + 1] - shift;
+          p1 += x0; p2 = fmaf(x0, x0, p2);
+          q1 += x1; q2 = fmaf(x1, x1, q2);
         }
       }
-      return acc0 + acc1;
+      s1 = p1 + q1;
+      s2 = p2 + q2;
     };
 
     uint32_t u = 0;
@@ -559,8 +619,10 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
         if (ew == 0 && lane == 0) trace(u, 3);
         const int col_base = static_cast<int>(crank) * kUnitN;
         const uint32_t taddr = tmem_base + lane_base + buf * kUnitN;
-        const float mean_h = unit_moment(taddr, col_base, kUnitN, 0.f, false) * (1.0f / kUnitN);
-        const float m2_h = unit_moment(taddr, col_base, kUnitN, mean_h, true);
+        float shift, s1, s2;
+        unit_shifted_sums(taddr, col_base, shift, s1, s2);
+        const float mean_h = shift + s1 * (1.0f / kUnitN);              // mean of my 256 columns
+        const float m2_h = fmaxf(s2 - s1 * s1 * (1.0f / kUnitN), 0.f);  // sum of squared deviations
         const int myrow = ew * 32 + lane;
         const uint32_t peer = crank ^ 1u;
         ptx::st_cluster_f32x2(ptx::mapa(ptx::smem_addr(&s_lnx[buf * kTileM + myrow]), peer), mean_h, m2_h);

@@ -55,6 +55,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Busy-polling wait (mbarrier.test_wait, no suspend): lowest wake-up latency; for the
+// single issuing lanes of the TMA / MMA warps, which have nothing else to do.
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_addr(bar);
+  uint32_t done = 0;
+#ifdef GCB_BOUNDED_WAIT
+  const long long t0 = clock64();
+#endif
+  for (;;) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+#ifdef GCB_BOUNDED_WAIT
+    if (clock64() - t0 > 3000000000ll) asm volatile("trap;");
+#endif
+  }
+}
+
 // ---- proxies / fences ---------------------------------------------------------
 // Make generic-proxy shared-memory writes (st.shared) visible to the async
 // proxy (tcgen05.mma operand reads, bulk copies).
@@ -76,6 +101,11 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
       ::"r"(smem_addr(smem_dst)),
       "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar))
       : "memory");
+}
+
+// Hint: bring [gmem_src, +bytes) into L2 (no shared-memory destination, no completion).
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
 }
 
 // Same, multicast to every CTA of the cluster selected by cta_mask: the bytes land at

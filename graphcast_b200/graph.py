@@ -48,8 +48,12 @@ class StaticGraph:
 
 def build_static_graph(*, grid_lat: np.ndarray, grid_lon: np.ndarray,
                        mesh_size: int, radius_query_fraction_edge_length: float,
-                       mesh2grid_edge_normalization_factor: Optional[float] = None
+                       mesh2grid_edge_normalization_factor: Optional[float] = None,
+                       connectivity: Optional[Dict[str, np.ndarray]] = None
                        ) -> StaticGraph:
+  """`connectivity` (optional) supplies the results of the two spatial queries
+  (`g2m_grid`, `g2m_mesh`, `m2g_grid`, `m2g_mesh` index arrays) so that they are
+  not recomputed; everything else is always derived here."""
   meshes = icosahedral_mesh.get_hierarchy_of_triangular_meshes_for_sphere(
       splits=mesh_size)
   finest = meshes[-1]
@@ -73,8 +77,11 @@ def build_static_graph(*, grid_lat: np.ndarray, grid_lon: np.ndarray,
   # grid2mesh (graphcast.py:264-267, 408-458).
   radius = (icosahedral_mesh.max_edge_length(finest)
             * radius_query_fraction_edge_length)
-  g_idx, m_idx = grid_mesh_connectivity.radius_query_indices(
-      grid_latitude=grid_lat, grid_longitude=grid_lon, mesh=finest, radius=radius)
+  if connectivity is not None:
+    g_idx, m_idx = connectivity["g2m_grid"], connectivity["g2m_mesh"]
+  else:
+    g_idx, m_idx = grid_mesh_connectivity.radius_query_indices(
+        grid_latitude=grid_lat, grid_longitude=grid_lon, mesh=finest, radius=radius)
   grid_feats, mesh_feats, g2m_edge = model_utils.get_bipartite_graph_spatial_features(
       senders_node_lat=grid_nodes_lat, senders_node_lon=grid_nodes_lon,
       receivers_node_lat=mesh_lat, receivers_node_lon=mesh_lon,
@@ -88,8 +95,11 @@ def build_static_graph(*, grid_lat: np.ndarray, grid_lon: np.ndarray,
   del mesh_feats2  # identical to mesh_feats; the processor does not embed nodes
 
   # mesh2grid (graphcast.py:499-548).
-  g_idx3, m_idx3 = grid_mesh_connectivity.in_mesh_triangle_indices(
-      grid_latitude=grid_lat, grid_longitude=grid_lon, mesh=finest)
+  if connectivity is not None:
+    g_idx3, m_idx3 = connectivity["m2g_grid"], connectivity["m2g_mesh"]
+  else:
+    g_idx3, m_idx3 = grid_mesh_connectivity.in_mesh_triangle_indices(
+        grid_latitude=grid_lat, grid_longitude=grid_lon, mesh=finest)
   _, _, m2g_edge = model_utils.get_bipartite_graph_spatial_features(
       senders_node_lat=mesh_lat, senders_node_lon=mesh_lon,
       receivers_node_lat=grid_nodes_lat, receivers_node_lon=grid_nodes_lon,
@@ -125,9 +135,11 @@ def cached_static_graph(*, grid_lat: np.ndarray, grid_lon: np.ndarray,
                         cache_dir: Optional[str] = None) -> StaticGraph:
   """`build_static_graph` with an on-disk .npz cache keyed by the arguments.
 
-  The cache is purely a start-up optimisation (the 0.25 degree graph takes
-  minutes to build on a cold host); a missing / unreadable file falls back to
-  building."""
+  Only the results of the two spatial queries (grid2mesh radius query and
+  mesh2grid containing-triangle lookup: 4 index arrays, a few MB compressed) are
+  cached - they dominate the build time; features are recomputed on load.  The
+  cache is purely a start-up optimisation: a missing / unreadable file falls
+  back to the full build."""
   import hashlib
   import os
   if cache_dir is None:
@@ -139,26 +151,26 @@ def cached_static_graph(*, grid_lat: np.ndarray, grid_lon: np.ndarray,
   h.update(np.ascontiguousarray(grid_lat, dtype=np.float32).tobytes())
   h.update(np.ascontiguousarray(grid_lon, dtype=np.float32).tobytes())
   h.update(repr((mesh_size, float(radius_query_fraction_edge_length),
-                 mesh2grid_edge_normalization_factor, "v1")).encode())
-  path = os.path.join(cache_dir, f"static_graph_{h.hexdigest()[:16]}.npz")
+                 mesh2grid_edge_normalization_factor, "v2")).encode())
+  path = os.path.join(cache_dir, f"connectivity_{h.hexdigest()[:16]}.npz")
+  build = lambda conn: build_static_graph(
+      grid_lat=grid_lat, grid_lon=grid_lon, mesh_size=mesh_size,
+      radius_query_fraction_edge_length=radius_query_fraction_edge_length,
+      mesh2grid_edge_normalization_factor=mesh2grid_edge_normalization_factor,
+      connectivity=conn)
   if os.path.exists(path):
     try:
       with np.load(path) as z:
-        return StaticGraph(num_grid_nodes=int(z["num_grid_nodes"]),
-                           num_mesh_nodes=int(z["num_mesh_nodes"]),
-                           **{k: z[k] for k in z.files
-                              if k not in ("num_grid_nodes", "num_mesh_nodes")})
+        conn = {k: z[k] for k in ("g2m_grid", "g2m_mesh", "m2g_grid", "m2g_mesh")}
+      return build(conn)
     except Exception:  # corrupt cache -> rebuild
       pass
-  g = build_static_graph(
-      grid_lat=grid_lat, grid_lon=grid_lon, mesh_size=mesh_size,
-      radius_query_fraction_edge_length=radius_query_fraction_edge_length,
-      mesh2grid_edge_normalization_factor=mesh2grid_edge_normalization_factor)
+  g = build(None)
   try:
     os.makedirs(cache_dir, exist_ok=True)
     tmp = path + f".tmp{os.getpid()}.npz"
-    np.savez(tmp, num_grid_nodes=g.num_grid_nodes, num_mesh_nodes=g.num_mesh_nodes,
-             **g.as_dict())
+    np.savez_compressed(tmp, g2m_grid=g.g2m_senders, g2m_mesh=g.g2m_receivers,
+                        m2g_grid=g.m2g_receivers, m2g_mesh=g.m2g_senders)
     os.replace(tmp, path)
   except OSError:
     pass

@@ -299,6 +299,10 @@ int gcb_profile_end(int32_t capacity, int32_t* kinds, float* ms, double* flops, 
  * [5] epilogue: tile stored. */
 int gcb_debug_trace(long long* device_buffer);
 
+/* Debug only: experiment switches of the tensor-core kernel (0 = production behaviour;
+ * non-zero values deliberately break results and exist for performance attribution). */
+int gcb_debug_flags(int flags);
+
 /* Device self-test of the tensor-core layer against the FP32_SIMT arm on random
  * data (used by tests and __graft_entry__.smoke); returns max |diff| / max |ref|
  * through *rel_err.  Allocates its own scratch. */

@@ -40,7 +40,7 @@ def run(rows, k, n, ln, act, csize, out_y=False, residual=False, idx=False, pre=
     d.n_pre_add = pre
     for i in range(pre):
       d.pre_add[i].table, d.pre_add[i].idx, d.pre_add[i].ld = ptab[i].data_ptr(), pidx[i].data_ptr(), 512
-  tr = torch.zeros(64 * 8, dtype=torch.int64, device=dev)
+  tr = torch.zeros(64 * 16, dtype=torch.int64, device=dev)
   for _ in range(2):
     lib.gcb_layer_forward(C.byref(d), None)
   torch.cuda.synchronize()
@@ -49,7 +49,7 @@ def run(rows, k, n, ln, act, csize, out_y=False, residual=False, idx=False, pre=
   e0.record(); lib.gcb_layer_forward(C.byref(d), None); e1.record()
   torch.cuda.synchronize()
   lib.gcb_debug_trace(None)
-  t = tr.cpu().numpy().reshape(64, 8)
+  t = tr.cpu().numpy().reshape(64, 16)
   ntile = min(64, (rows + 127) // 128 // 148)
   print(f"rows={rows} k={k} n={n} ln={ln} act={act} cluster={csize} out_y={out_y} res={residual} idx={idx} pre={pre} img_in={img_in} img_out={img_out}: {e0.elapsed_time(e1):.3f} ms; tiles/CTA~{ntile}")
   base = t[1, 0]
@@ -57,13 +57,35 @@ def run(rows, k, n, ln, act, csize, out_y=False, residual=False, idx=False, pre=
     r = t[i]
     print(f"  tile {i}: acc_free@{r[0]-base:7d} ops_ready+{r[1]-r[0]:6d} mma_issue+{r[2]-r[1]:6d} | "
           f"epi_start(after commit)+{r[3]-r[2]:6d} ln_stats+{r[4]-r[3]:6d} store+{r[5]-r[4]:6d} | "
-          f"next_acc_free+{t[i+1,0]-r[5]:6d}  tile_total={t[i+1,0]-r[0]}")
+          f"next_acc_free+{t[i+1,0]-r[5]:6d}  tile_total={t[i+1,0]-r[0]} | mma_starved={r[6]} tma_blocked={r[7]} tma_head={r[8]} expect={r[9]} acopy={r[10]} bcopy={r[11]}")
 
-rows = 148 * 128 * 8
+import sys
+big = len(sys.argv) > 1 and sys.argv[1] in ("big", "flags", "cluster")
+if len(sys.argv) > 1 and sys.argv[1] == "cluster":
+  for cs in (1, 2):
+    for fl in (0, 2):
+      print("== cluster", cs, "flags", fl)
+      lib.gcb_debug_flags(fl)
+      run(148 * 128 * 160, 512, 512, False, True, cs, img_in=True, img_out=True)
+      run(148 * 128 * 160, 512, 512, True, False, cs, img_in=True)
+  lib.gcb_debug_flags(0)
+  sys.exit(0)
+rows = 148 * 128 * (160 if big else 8)
+if len(sys.argv) > 1 and sys.argv[1] == "flags":
+  # attribution sweep: 1 A from tile 0 (L2 hits) | 2 no stores | 4 no A multicast |
+  # 8 B block 0 only | 16 L2 prefetch | 32 no A load
+  for fl in (0, 1, 2, 3, 4, 8, 32, 1 | 2 | 8, 32 | 2 | 8):
+    print(f"==== debug flags {fl}")
+    lib.gcb_debug_flags(fl)
+    run(rows, 512, 512, False, True, 2, img_in=True, img_out=True)
+    run(rows, 512, 512, True, False, 2, img_in=True)
+  lib.gcb_debug_flags(0)
+  sys.exit(0)
 for cs in (2,):
-  run(rows, 512, 512, False, True, cs, img_out=True)
   run(rows, 512, 512, False, True, cs, img_in=True, img_out=True)
-  run(rows, 512, 512, False, True, cs, pre=2, img_in=True, img_out=True)
   run(rows, 512, 512, True, False, cs, img_in=True)
-  run(rows, 512, 512, True, False, cs, out_y=True, residual=True, img_in=True)
-  run(rows, 1536, 512, False, True, cs, idx=True, img_out=True)
+  if not big:
+    run(rows, 512, 512, False, True, cs, img_out=True)
+    run(rows, 512, 512, False, True, cs, pre=2, img_in=True, img_out=True)
+    run(rows, 512, 512, True, False, cs, out_y=True, residual=True, img_in=True)
+    run(rows, 1536, 512, False, True, cs, idx=True, img_out=True)
