@@ -241,7 +241,7 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
       ptx::mbar_init(&tmem_empty_bar[b], 4);   // 4 epilogue warps
       ptx::mbar_init(&g_full_bar[b], 4);       // 4 warps of one producer group
       ptx::mbar_init(&g_empty_bar[b], 4);      // 4 epilogue warps
-      ptx::mbar_init(&lnx_bar[b], 128);        // every epilogue thread of the partner CTA
+      ptx::mbar_init(&lnx_bar[b], 1);          // my expect_tx; the partner's 128 st.async complete it
     }
     ptx::fence_mbar_init();
   }
@@ -625,9 +625,10 @@ mlp_layer_tc_kernel(const __grid_constant__ gcb_layer_desc d) {
         const float m2_h = fmaxf(s2 - s1 * s1 * (1.0f / kUnitN), 0.f);  // sum of squared deviations
         const int myrow = ew * 32 + lane;
         const uint32_t peer = crank ^ 1u;
-        ptx::st_cluster_f32x2(ptx::mapa(ptx::smem_addr(&s_lnx[buf * kTileM + myrow]), peer), mean_h, m2_h);
-        ptx::mbar_arrive_remote(ptx::mapa(ptx::smem_addr(&lnx_bar[buf]), peer));
-        ptx::mbar_wait_cluster(&lnx_bar[buf], par);
+        ptx::st_async_f32x2(ptx::mapa(ptx::smem_addr(&s_lnx[buf * kTileM + myrow]), peer), mean_h, m2_h,
+                            ptx::mapa(ptx::smem_addr(&lnx_bar[buf]), peer));
+        if (ew == 0 && lane == 0) ptx::mbar_arrive_expect_tx(&lnx_bar[buf], kTileM * 8);
+        ptx::mbar_wait(&lnx_bar[buf], par);
         const float2 other = s_lnx[buf * kTileM + myrow];
         const float delta = other.x - mean_h;
         const float mean = 0.5f * (mean_h + other.x);

@@ -157,6 +157,14 @@ __device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
 __device__ __forceinline__ void st_cluster_f32x2(uint32_t raddr, float a, float b) {
   asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(raddr), "f"(a), "f"(b) : "memory");
 }
+// Asynchronous 8-byte store into another CTA's shared memory that signals that CTA's
+// mbarrier (complete_tx, 8 bytes) when the data is visible there.  No release fence in the
+// sender: a per-thread `mbarrier.arrive.release.cluster` drains the thread's outstanding
+// global stores first (ERRBAR + MEMBAR: 11 % of the LayerNorm epilogue's time in ncu).
+__device__ __forceinline__ void st_async_f32x2(uint32_t raddr, float a, float b, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(raddr), "f"(a), "f"(b), "r"(rbar) : "memory");
+}
 // Arrive (release at cluster scope) on an mbarrier of another CTA of the cluster.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t raddr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
