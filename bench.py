@@ -42,6 +42,7 @@ WORKLOADS = {
     "tiny_4deg_13lvl": (4.0, 3, "TASK_13"),
 }
 DEFAULT_WORKLOAD = "graphcast_0.25deg_37lvl"
+REFERENCE_BUDGET_S = 150.0   # wall-clock target of a whole `--impl reference` run
 
 
 def algorithmic_flops(ng, nm, e1, e2, e3, c_in, n_out, steps, d=512):
@@ -124,6 +125,14 @@ def run_reference(args):
   torch.set_num_threads(cores)
   res, mesh, task_name = WORKLOADS[args.workload]
   task = getattr(graphcast, task_name)
+  # Bounded sample: every step is one full oracle pass over a reduced-resolution instance of
+  # the same model, scaled by algorithmic FLOPs.  The whole --steps/--warmup run must end
+  # within a few minutes, so fall back to the smaller sample when the requested one would
+  # not fit REFERENCE_BUDGET_S (an oracle pass over the 2 degree sample takes 30-65 s).
+  cpu_sample = args.cpu_sample
+  if cpu_sample == "sample_2deg_13lvl" and (args.steps + args.warmup) * 65.0 > REFERENCE_BUDGET_S:
+    cpu_sample = "tiny_4deg_13lvl"
+  args.cpu_sample = cpu_sample
   s_res, s_mesh, s_task_name = WORKLOADS[args.cpu_sample]
   s_task = getattr(graphcast, s_task_name)
   lat, lon = synthetic.grid_coords(s_res)

@@ -141,18 +141,35 @@ pack_grid_image_kernel(const float* __restrict__ planes, int n_ch, long long n_n
   const long long node0 = static_cast<long long>(blockIdx.x) * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long node = node0 + lane;
-  for (int c = warp; c < k; c += 8) {
-    float v = 0.f;
-    if (node < n_nodes) {
+  // Phase 1 is pure latency (one 128-byte line per warp and channel): keep kU independent
+  // plane loads in flight per warp instead of one.
+  constexpr int kU = 6;
+  for (int c0 = warp; c0 < k; c0 += 8 * kU) {
+    float v[kU], mu[kU], sd[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int c = c0 + 8 * u;
+      v[u] = 0.f; mu[u] = 0.f; sd[u] = 1.f;
       if (c < n_ch) {
-        v = planes[static_cast<long long>(c) * n_nodes + node];
-        if (mean) v -= mean[c];
-        if (scale) v /= scale[c];
-      } else if (c < n_ch + n_static) {
-        v = node_static[node * n_static + (c - n_ch)];
+        if (node < n_nodes) v[u] = planes[static_cast<long long>(c) * n_nodes + node];
+        if (mean) mu[u] = mean[c];
+        if (scale) sd[u] = scale[c];
+      } else if (c < n_ch + n_static && node < n_nodes) {
+        v[u] = node_static[node * n_static + (c - n_ch)];
       }
     }
-    tile[lane * kp + c] = v;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int c = c0 + 8 * u;
+      if (c < k) {
+        float x = v[u];
+        if (c < n_ch && node < n_nodes) {
+          if (mean) x -= mu[u];
+          if (scale) x /= sd[u];
+        }
+        tile[lane * kp + c] = x;
+      }
+    }
   }
   __syncthreads();
   const long long t = node >> 7;
