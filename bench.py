@@ -28,6 +28,12 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv:
+  # The CPU arm uses every host thread; torchrun exports OMP_NUM_THREADS=1 to its workers,
+  # which would silently make it single-threaded.  Must happen before numpy / torch load.
+  for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))
@@ -122,7 +128,6 @@ def run_reference(args):
   from graphcast_b200 import graph as graph_lib, graphcast, synthetic
   from oracle import gnn as oracle_gnn
   cores = os.cpu_count() or 1
-  torch.set_num_threads(cores)
   res, mesh, task_name = WORKLOADS[args.workload]
   task = getattr(graphcast, task_name)
   # Bounded sample: every step is one full oracle pass over a reduced-resolution instance of
@@ -150,6 +155,18 @@ def run_reference(args):
   full = full_workload_sizes(args.workload)
   full_flops = algorithmic_flops(*full)
   scale = full_flops / sample_flops
+  # Thread count: the oracle's torch ops stop scaling (and regress) well before 128 threads on
+  # the GPU boxes' hosts, so calibrate on one pass each and keep the fastest.
+  best = None
+  for nthreads in sorted({cores, min(cores, 32), min(cores, 16)}, reverse=True):
+    torch.set_num_threads(nthreads)
+    tc = time.perf_counter()
+    orc.forward(gd, x)
+    tc = time.perf_counter() - tc
+    if best is None or tc < best[0]:
+      best = (tc, nthreads)
+  cores = best[1]
+  torch.set_num_threads(cores)
   for _ in range(args.warmup):
     orc.forward(gd, x)
   t0 = time.perf_counter()
@@ -210,12 +227,17 @@ def cpu_baseline_sample(args, torch):
   sample_flops = algorithmic_flops(g.num_grid_nodes, g.num_mesh_nodes, len(g.g2m_senders),
                                    len(g.mesh_senders), len(g.m2g_senders), c_in, n_out, 16)
   full_flops = algorithmic_flops(*full_workload_sizes(args.workload))
-  orc.forward(gd, x)                      # warm-up (page faults, MKL threads)
-  t0 = time.perf_counter()
-  reps = 1
-  for _ in range(reps):
+  # Two full passes: all host threads (also the page-fault warm-up), then at most 32 threads -
+  # the oracle's torch ops regress with 128 threads on the GPU boxes' hosts.  Report the faster.
+  dt = None
+  for nthreads in (cores, min(cores, 32)):
+    torch.set_num_threads(nthreads)
+    t0 = time.perf_counter()
     orc.forward(gd, x)
-  dt = (time.perf_counter() - t0) / reps
+    t = time.perf_counter() - t0
+    if dt is None or t < dt:
+      dt, used = t, nthreads
+  cores = used
   scale = full_flops / sample_flops
   return {"value": 1.0 / (dt * scale), "unit": "steps/s", "cores": cores, "kind": "port",
           "sample": (f"{args.cpu_sample}: full fp32 oracle step ({sample_flops/1e12:.2f} TFLOP, "
