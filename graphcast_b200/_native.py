@@ -102,6 +102,7 @@ EXPORTS = {
                                           _fp, _fp, _fp]),
     "gcb_forward": (C.c_int, [C.POINTER(Model), _fp, _fp, _fp, C.POINTER(C.c_int32)]),
     "gcb_set_cluster_size": (C.c_int, [C.c_int32]),
+    "gcb_set_graph_replay": (C.c_int, [C.c_int32]),
     "gcb_debug_trace": (C.c_int, [_fp]),
     "gcb_debug_flags": (C.c_int, [C.c_int]),
     "gcb_profile_begin": (C.c_int, []),
@@ -140,6 +141,8 @@ def lib():
     fn.argtypes = argtypes
   if handle.gcb_abi_version() != GCB_ABI_VERSION:
     raise NativeLibraryError("ABI version mismatch between _native.py and the library")
+  if os.environ.get("GCB_NO_GRAPH"):      # debugging aid: plain launches instead of graph replay
+    handle.gcb_set_graph_replay(0)
   _lib = handle
   return _lib
 

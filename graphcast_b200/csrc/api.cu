@@ -429,9 +429,24 @@ int gcb_segment_sum(const float* msg, int32_t ld_msg, const int32_t* row_ptr, in
   return gcb_segment_sum_heavy(msg, ld_msg, row_ptr, num_nodes, nullptr, 0, out, ld_out, width, stream);
 }
 
+namespace {
+int segment_sum_launch(const float* msg, int32_t ld_msg, const int32_t* row_ptr, int32_t num_nodes,
+                       const int32_t* heavy, int32_t num_heavy, float* out, int32_t ld_out,
+                       int32_t width, void* img, void* stream);
+}
+
 int gcb_segment_sum_heavy(const float* msg, int32_t ld_msg, const int32_t* row_ptr,
                           int32_t num_nodes, const int32_t* heavy, int32_t num_heavy, float* out,
                           int32_t ld_out, int32_t width, void* stream) {
+  return segment_sum_launch(msg, ld_msg, row_ptr, num_nodes, heavy, num_heavy, out, ld_out, width,
+                            nullptr, stream);
+}
+
+namespace {
+// img (optional): operand image of the [num_nodes, 512] result, written by the same kernel.
+int segment_sum_launch(const float* msg, int32_t ld_msg, const int32_t* row_ptr, int32_t num_nodes,
+                       const int32_t* heavy, int32_t num_heavy, float* out, int32_t ld_out,
+                       int32_t width, void* img, void* stream) {
   GCB_CHECK_ARG(msg && row_ptr && out, "null pointer");
   GCB_CHECK_ARG(num_heavy >= 0 && (num_heavy == 0 || heavy != nullptr), "heavy list is null");
   GCB_CHECK_ARG(width == 512, "segment_sum supports width 512");
@@ -445,10 +460,12 @@ int gcb_segment_sum_heavy(const float* msg, int32_t ld_msg, const int32_t* row_p
                  4.0 * width * (static_cast<double>(num_nodes) + 0.0) + 0.0);
   gcb::segment_sum_kernel<4><<<static_cast<int>(blocks) + num_heavy, 256, 0,
                               static_cast<cudaStream_t>(stream)>>>(
-      msg, ld_msg, row_ptr, num_nodes, out, ld_out, heavy, num_heavy);
+      msg, ld_msg, row_ptr, num_nodes, out, ld_out, heavy, num_heavy,
+      static_cast<unsigned char*>(img));
   GCB_CUDA(cudaGetLastError());
   return GCB_OK;
 }
+}  // namespace
 
 int gcb_pack_grid_features(const float* planes, int32_t n_ch, int64_t n_nodes, const float* mean,
                            const float* scale, const float* node_static, int32_t n_static,
@@ -530,9 +547,102 @@ int gcb_rows_to_image(const float* src, int32_t ld, int32_t fan, int64_t rows, i
   return GCB_OK;
 }
 
+namespace {
+
+// One recorded step per (model, buffers, stream): gcb_forward runs eagerly the first time it
+// sees a key (attribute / occupancy queries happen there), captures the same launch sequence
+// into a CUDA graph the second time, and replays it afterwards.
+struct StepGraph {
+  std::vector<unsigned char> key;
+  cudaGraphExec_t exec = nullptr;
+  int launches = 0;
+};
+std::vector<StepGraph> g_step_graphs;
+bool g_graph_replay = true;
+
+void drop_step_graphs() {
+  for (auto& g : g_step_graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  g_step_graphs.clear();
+}
+
+int forward_eager(const gcb_model* m, const void* grid_in_img, float* grid_out, void* stream,
+                  int32_t* launches);
+
+}  // namespace
+
+int gcb_set_graph_replay(int32_t enabled) {
+  g_graph_replay = enabled != 0;
+  if (!g_graph_replay) drop_step_graphs();
+  return GCB_OK;
+}
+
 int gcb_forward(const gcb_model* m, const void* grid_in_img, float* grid_out, void* stream,
                 int32_t* launches) {
   GCB_CHECK_ARG(m && grid_in_img && grid_out, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  bool replay = g_graph_replay && !g_prof_on && st != nullptr && st != cudaStreamLegacy &&
+                st != cudaStreamPerThread;
+  if (replay) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+      cudaGetLastError();
+      replay = false;               // the caller is capturing: just contribute the launches
+    }
+  }
+  if (!replay) return forward_eager(m, grid_in_img, grid_out, stream, launches);
+
+  std::vector<unsigned char> key(sizeof(gcb_model) + 4 * sizeof(void*));
+  memcpy(key.data(), m, sizeof(gcb_model));
+  const void* extra[4] = {grid_in_img, grid_out, stream,
+                          reinterpret_cast<const void*>(static_cast<intptr_t>(g_cluster_size))};
+  memcpy(key.data() + sizeof(gcb_model), extra, sizeof(extra));
+  StepGraph* g = nullptr;
+  for (auto& e : g_step_graphs)
+    if (e.key == key) { g = &e; break; }
+  int32_t n = 0;
+  if (g == nullptr) {
+    const int rc = forward_eager(m, grid_in_img, grid_out, stream, &n);
+    if (rc != GCB_OK) return rc;
+    if (g_step_graphs.size() >= 8) {
+      if (g_step_graphs.front().exec) cudaGraphExecDestroy(g_step_graphs.front().exec);
+      g_step_graphs.erase(g_step_graphs.begin());
+    }
+    StepGraph e;
+    e.key = std::move(key);
+    e.launches = n;
+    g_step_graphs.push_back(std::move(e));
+    if (launches) *launches = n;
+    return GCB_OK;
+  }
+  if (g->exec == nullptr) {
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      g_graph_replay = false;
+      return forward_eager(m, grid_in_img, grid_out, stream, launches);
+    }
+    const int rc = forward_eager(m, grid_in_img, grid_out, stream, &n);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (rc == GCB_OK && e == cudaSuccess) e = cudaGraphInstantiate(&g->exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != GCB_OK || e != cudaSuccess) {
+      cudaGetLastError();
+      g->exec = nullptr;
+      g_graph_replay = false;       // never retry; fall back to plain launches
+      if (rc != GCB_OK) return rc;
+      return forward_eager(m, grid_in_img, grid_out, stream, launches);
+    }
+  }
+  GCB_CUDA(cudaGraphLaunch(g->exec, st));
+  if (launches) *launches = g->launches;
+  return GCB_OK;
+}
+
+namespace {
+
+int forward_eager(const gcb_model* m, const void* grid_in_img, float* grid_out, void* stream,
+                  int32_t* launches) {
   GCB_CHECK_ARG(m->msg_steps >= 1 && m->msg_steps <= GCB_MAX_MSG_STEPS, "msg_steps out of range");
   GCB_CHECK_ARG(m->e_m2g == 3 * m->num_grid, "mesh2grid must have fan-in 3");
   GCB_CHECK_ARG(m->hidden && m->edge_a_img && m->edge_b && m->mesh_in_img &&
@@ -569,10 +679,9 @@ int gcb_forward(const gcb_model* m, const void* grid_in_img, float* grid_out, vo
                          m->mesh_lat, m->mesh_lat_img, m->num_mesh, m->g2m_rcv, m->proj_mesh_a, o)))
     return rc;
   // agg1 = segment_sum(m1)
-  if ((rc = gcb_segment_sum_heavy(m->edge_b, D, m->g2m_row_ptr, m->num_mesh, m->g2m_heavy,
-                                  m->n_g2m_heavy, m->mesh_agg, D, D, stream))) return rc;
+  if ((rc = segment_sum_launch(m->edge_b, D, m->g2m_row_ptr, m->num_mesh, m->g2m_heavy,
+                               m->n_g2m_heavy, m->mesh_agg, D, D, m->mesh_agg_img, stream))) return rc;
   c.launches += 1;
-  if ((rc = to_image(c, m->mesh_agg, D, 1, m->num_mesh, D, m->mesh_agg_img))) return rc;
   // vm1 = vm0 + LN.MLP([vm0 | agg1])  (in place)
   s[0] = seg_img(m->mesh_lat_img, D);
   s[1] = seg_img(m->mesh_agg_img, D);
@@ -597,9 +706,9 @@ int gcb_forward(const gcb_model* m, const void* grid_in_img, float* grid_out, vo
                            m->mesh_lat, m->mesh_lat_img, m->num_mesh, m->mesh_snd, m->proj_mesh_a,
                            m->mesh_lat, m->mesh_lat_img, m->num_mesh, m->mesh_rcv, m->proj_mesh_b, o)))
       return rc;
-    if ((rc = gcb_segment_sum(m->mesh_msg, D, m->mesh_row_ptr, m->num_mesh, m->mesh_agg, D, D, stream))) return rc;
+    if ((rc = segment_sum_launch(m->mesh_msg, D, m->mesh_row_ptr, m->num_mesh, nullptr, 0, m->mesh_agg,
+                                 D, D, m->mesh_agg_img, stream))) return rc;
     c.launches += 1;
-    if ((rc = to_image(c, m->mesh_agg, D, 1, m->num_mesh, D, m->mesh_agg_img))) return rc;
     // v += LN.MLP([v | agg])
     s[0] = seg_img(m->mesh_lat_img, D);
     s[1] = seg_img(m->mesh_agg_img, D);
@@ -632,6 +741,8 @@ int gcb_forward(const gcb_model* m, const void* grid_in_img, float* grid_out, vo
   if (launches) *launches = c.launches;
   return GCB_OK;
 }
+
+}  // namespace
 
 int gcb_set_cluster_size(int32_t ctas) {
   GCB_CHECK_ARG(ctas == 1 || ctas == 2 || ctas == 4, "cluster size must be 1, 2 or 4");

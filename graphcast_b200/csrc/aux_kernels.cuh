@@ -4,6 +4,8 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include "ptx.cuh"
+
 namespace gcb {
 
 // out[node, :] = sum over in-edges (CSR row_ptr, edges receiver-sorted) of msg[e, :].
@@ -18,11 +20,25 @@ namespace gcb {
 // deterministic).
 constexpr int kHeavyDegree = 256;
 
+// Four consecutive columns (col % 4 == 0) of row `row` into an operand image of a [rows, k]
+// matrix: 8 bytes of bf16 "hi" and 8 bytes of "lo" (layout: GCB_A_IMAGE_BLOCK, graphcast_b200.h).
+__device__ __forceinline__ void store_image_f4(unsigned char* img, long long row, int col, int k,
+                                               const float4& v) {
+  uint2 hi, lo;
+  ptx::split_bf16x4(v, hi, lo);
+  unsigned char* dst = img + (static_cast<size_t>(row >> 7) * (k >> 4) + (col >> 4)) * 8448 +
+                       ((col >> 3) & 1) * 2112 + (row & 127) * 16 + (col & 7) * 2;
+  *reinterpret_cast<uint2*>(dst) = hi;
+  *reinterpret_cast<uint2*>(dst + 4224) = lo;
+}
+
+// `img` (optional): also emit the sums as an operand image of the [num_nodes, 128*kVecPerLane]
+// result, so that the consuming layer needs no separate conversion pass.
 template <int kVecPerLane>
 __global__ void __launch_bounds__(256)
 segment_sum_kernel(const float* __restrict__ msg, int ld_msg, const int* __restrict__ row_ptr,
                    int num_nodes, float* __restrict__ out, int ld_out,
-                   const int* __restrict__ heavy, int num_heavy) {
+                   const int* __restrict__ heavy, int num_heavy, unsigned char* __restrict__ img) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int light_blocks = gridDim.x - num_heavy;
@@ -52,6 +68,7 @@ segment_sum_kernel(const float* __restrict__ msg, int ld_msg, const int* __restr
       float4 s = part[0][i];
       for (int k = 1; k < 8; ++k) { s.x += part[k][i].x; s.y += part[k][i].y; s.z += part[k][i].z; s.w += part[k][i].w; }
       reinterpret_cast<float4*>(out + static_cast<long long>(node) * ld_out)[i] = s;
+      if (img) store_image_f4(img, node, 4 * i, 128 * kVecPerLane, s);
     }
     return;
   }
@@ -87,6 +104,11 @@ segment_sum_kernel(const float* __restrict__ msg, int ld_msg, const int* __restr
     float4* po = reinterpret_cast<float4*>(out + node * ld_out);
 #pragma unroll
     for (int j = 0; j < kVecPerLane; ++j) po[lane + 32 * j] = acc[j];
+    if (img) {
+#pragma unroll
+      for (int j = 0; j < kVecPerLane; ++j)
+        store_image_f4(img, node, 4 * (lane + 32 * j), 128 * kVecPerLane, acc[j]);
+    }
   }
 }
 

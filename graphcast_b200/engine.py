@@ -54,6 +54,7 @@ class Engine:
       raise ValueError(f"unknown precision {precision!r}; expected one of "
                        f"{sorted(_native.PRECISIONS)}")
     self._lib = _native.lib()            # raises if the CUDA library is missing
+    self._step_stream = None             # created on first use (see step)
     if not torch.cuda.is_available():
       raise RuntimeError("graphcast_b200 requires a CUDA device (no CPU fallback)")
     self.device = torch.device(device if device is not None else
@@ -233,7 +234,8 @@ class Engine:
 
   # -- workspace ---------------------------------------------------------------------
   def _image(self, rows: int, k: int = LATENT) -> torch.Tensor:
-    return torch.empty([self._lib.gcb_a_image_bytes(max(rows, 1), k)], dtype=torch.uint8,
+    # zeros: rows of the last 128-row tile beyond `rows` are never written by some producers
+    return torch.zeros([self._lib.gcb_a_image_bytes(max(rows, 1), k)], dtype=torch.uint8,
                        device=self.device)
 
   def _alloc_workspace(self) -> None:
@@ -308,9 +310,20 @@ class Engine:
     grid_in = self.grid_in_img if grid_in is None else grid_in
     grid_out = self.grid_out if grid_out is None else grid_out
     n = C.c_int32(0)
+    cur = torch.cuda.current_stream(self.device)
+    # The step replays a CUDA graph (gcb_set_graph_replay), which the legacy default stream
+    # cannot capture: run it on the engine's own stream, fenced against the current one.
+    side = cur.cuda_stream == 0
+    if side:
+      if self._step_stream is None:
+        self._step_stream = torch.cuda.Stream(self.device)
+      self._step_stream.wait_stream(cur)
+    st = self._step_stream if side else cur
     _native.check(self._lib.gcb_forward(C.byref(self._model), grid_in.data_ptr(),
-                                        grid_out.data_ptr(), self._stream(), C.byref(n)),
+                                        grid_out.data_ptr(), st.cuda_stream, C.byref(n)),
                   "gcb_forward")
+    if side:
+      cur.wait_stream(self._step_stream)
     self.launches_per_step = int(n.value)
     return grid_out
 

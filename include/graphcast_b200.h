@@ -277,6 +277,13 @@ typedef struct {
 int gcb_forward(const gcb_model* m, const void* grid_in_img, float* grid_out, void* stream,
                 int32_t* launches);
 
+/* gcb_forward replays a CUDA graph of its launch sequence from the third call with the same
+ * (model contents, buffers, stream) on: the first call runs the launches directly, the second
+ * captures them.  Needs a non-legacy stream (a NULL / legacy / per-thread default stream, an
+ * active gcb_profile_begin, or a caller that is itself capturing all fall back to direct
+ * launches).  Not thread-safe.  enabled = 0 disables replay and drops the recorded graphs. */
+int gcb_set_graph_replay(int32_t enabled);
+
 /* Per-launch profiling.  Between gcb_profile_begin() and gcb_profile_end() every
  * kernel launched through this ABI is bracketed by CUDA events on its stream.
  * gcb_profile_end synchronises them and returns, per launch (in launch order,

@@ -32,7 +32,8 @@ def test_step_matches_oracle(prec, tol, pregather):
   assert _rel(y, ref) <= tol
   mlp_layers = 2 * (6 + 1 + 2 * 3 + 4)
   projections = 2 * (1 + 3 + 1) if pregather else 0       # two per edge MLP (g2m, 3 mesh steps, m2g)
-  to_image = 1 + 3 + 1                  # agg1, 3 x mesh agg, summed m2g messages
+  to_image = 1                          # summed m2g messages (the mesh aggregates' images are
+                                        # written by the segment-sum kernel itself)
   assert eng.launches_per_step == mlp_layers + projections + (1 + 3) + to_image   # + segment sums
 
 
@@ -52,6 +53,28 @@ def test_determinism_bitwise():
   a = eng.forward_features(torch.as_tensor(x)).clone()
   b = eng.forward_features(torch.as_tensor(x)).clone()
   assert torch.equal(a, b)
+
+
+def test_graph_replay_is_bitwise_identical_to_direct_launches():
+  """gcb_forward: call 1 launches directly, call 2 captures a CUDA graph, calls 3+ replay it."""
+  from graphcast_b200 import _native
+  lib = _native.lib()
+  g, params, x = _cases.small_case(c_in=31, n_out=23, msg_steps=2)
+  eng = engine.Engine(g, params, c_in=31, n_out=23, msg_steps=2, precision="bf16x3")
+  xt = torch.as_tensor(x)
+  _native.check(lib.gcb_set_graph_replay(0), "gcb_set_graph_replay")
+  ref = eng.forward_features(xt).clone()
+  _native.check(lib.gcb_set_graph_replay(1), "gcb_set_graph_replay")
+  outs = [eng.forward_features(xt).clone() for _ in range(4)]   # direct, capture, replay, replay
+  for o in outs:
+    assert torch.equal(o, ref)
+  # new inputs through the replayed graph (same buffers, new contents)
+  x2 = torch.as_tensor(np.random.default_rng(7).standard_normal(x.shape).astype(np.float32))
+  got = eng.forward_features(x2).clone()
+  _native.check(lib.gcb_set_graph_replay(0), "gcb_set_graph_replay")
+  want = eng.forward_features(x2).clone()
+  _native.check(lib.gcb_set_graph_replay(1), "gcb_set_graph_replay")
+  assert torch.equal(got, want)
 
 
 def _task_example(batch=2, res=10.0, steps=1):
