@@ -133,9 +133,9 @@ def run_reference(args):
   # Bounded sample: every step is one full oracle pass over a reduced-resolution instance of
   # the same model, scaled by algorithmic FLOPs.  The whole --steps/--warmup run must end
   # within a few minutes, so fall back to the smaller sample when the requested one would
-  # not fit REFERENCE_BUDGET_S (an oracle pass over the 2 degree sample takes 30-65 s).
+  # not fit REFERENCE_BUDGET_S (an oracle pass over the 2 degree sample takes 4.5 s with 32 threads on a GPU box's host, 30 s on an 8-core VM).
   cpu_sample = args.cpu_sample
-  if cpu_sample == "sample_2deg_13lvl" and (args.steps + args.warmup) * 65.0 > REFERENCE_BUDGET_S:
+  if cpu_sample == "sample_2deg_13lvl" and (args.steps + args.warmup + 2) * 8.0 > REFERENCE_BUDGET_S:
     cpu_sample = "tiny_4deg_13lvl"
   args.cpu_sample = cpu_sample
   s_res, s_mesh, s_task_name = WORKLOADS[args.cpu_sample]
@@ -155,10 +155,10 @@ def run_reference(args):
   full = full_workload_sizes(args.workload)
   full_flops = algorithmic_flops(*full)
   scale = full_flops / sample_flops
-  # Thread count: the oracle's torch ops stop scaling (and regress) well before 128 threads on
-  # the GPU boxes' hosts, so calibrate on one pass each and keep the fastest.
+  # Thread count: the oracle's torch ops regress badly with 128 threads on the GPU boxes' hosts
+  # (64 s per 2-degree pass against 4.5 s with 32), so calibrate on one pass each, keep the fastest.
   best = None
-  for nthreads in sorted({cores, min(cores, 32), min(cores, 16)}, reverse=True):
+  for nthreads in thread_candidates(cores):
     torch.set_num_threads(nthreads)
     tc = time.perf_counter()
     orc.forward(gd, x)
@@ -207,6 +207,14 @@ def full_workload_sizes(name):
           graphcast.num_outputs(task), 16)
 
 
+def thread_candidates(cores):
+  """Thread counts worth trying for the torch-CPU oracle, most promising first."""
+  c = [min(cores, 32), min(cores, 16)]
+  if cores <= 64:
+    c.append(cores)
+  return sorted(set(c), reverse=True)
+
+
 def cpu_baseline_sample(args, torch):
   """Bounded CPU sample on rank 0 (reported beside the GPU number)."""
   from graphcast_b200 import graph as graph_lib, graphcast, synthetic
@@ -227,10 +235,10 @@ def cpu_baseline_sample(args, torch):
   sample_flops = algorithmic_flops(g.num_grid_nodes, g.num_mesh_nodes, len(g.g2m_senders),
                                    len(g.mesh_senders), len(g.m2g_senders), c_in, n_out, 16)
   full_flops = algorithmic_flops(*full_workload_sizes(args.workload))
-  # Two full passes: all host threads (also the page-fault warm-up), then at most 32 threads -
-  # the oracle's torch ops regress with 128 threads on the GPU boxes' hosts.  Report the faster.
+  # One full pass per candidate thread count (the first doubles as the page-fault warm-up);
+  # report the fastest.  128 threads are not tried: 64 s per pass against 4.5 s with 32.
   dt = None
-  for nthreads in (cores, min(cores, 32)):
+  for nthreads in thread_candidates(cores):
     torch.set_num_threads(nthreads)
     t0 = time.perf_counter()
     orc.forward(gd, x)
