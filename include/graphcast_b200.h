@@ -306,8 +306,10 @@ int gcb_profile_end(int32_t capacity, int32_t* kinds, float* ms, double* flops, 
  * [5] epilogue: tile stored. */
 int gcb_debug_trace(long long* device_buffer);
 
-/* Debug only: experiment switches of the tensor-core kernel (0 = production behaviour;
- * non-zero values deliberately break results and exist for performance attribution). */
+/* Debug only: experiment switches of the tensor-core kernel for performance attribution
+ * (0 = production behaviour).  2: skip all global stores of the epilogue (results are NOT
+ * produced); 4: N-split pairs stream the whole A block per CTA instead of multicasting halves
+ * (same results); 16: L2-prefetch the A blocks of the next tile (same results). */
 int gcb_debug_flags(int flags);
 
 /* Device self-test of the tensor-core layer against the FP32_SIMT arm on random

@@ -58,3 +58,31 @@ def test_in_mesh_triangle_is_closest_face():
   for i in range(n):
     fi = face_of[tuple(chosen[i])]
     assert d2[i, fi] <= d2[i].min() + 1e-12
+
+
+def test_cached_static_graph_round_trip(tmp_path):
+  """The on-disk cache keeps only the two spatial-query results; a graph rebuilt from it must
+  equal a fresh build bit for bit, and a corrupt cache file must fall back to building."""
+  import dataclasses
+  import os
+  from graphcast_b200 import graph as graph_lib
+  lat = np.linspace(-90, 90, 19, dtype=np.float32)
+  lon = np.arange(0, 360, 10, dtype=np.float32)
+  kw = dict(grid_lat=lat, grid_lon=lon, mesh_size=2, radius_query_fraction_edge_length=0.6)
+  fresh = graph_lib.build_static_graph(**kw)
+  first = graph_lib.cached_static_graph(cache_dir=str(tmp_path), **kw)     # builds + writes
+  files = os.listdir(tmp_path)
+  assert len(files) == 1 and files[0].startswith("connectivity_")
+  again = graph_lib.cached_static_graph(cache_dir=str(tmp_path), **kw)     # reads
+  for f in dataclasses.fields(fresh):
+    a, b, c = (getattr(x, f.name) for x in (fresh, first, again))
+    if isinstance(a, np.ndarray):
+      assert a.dtype == b.dtype == c.dtype
+      np.testing.assert_array_equal(a, b)
+      np.testing.assert_array_equal(a, c)
+    else:
+      assert a == b == c
+  with open(os.path.join(tmp_path, files[0]), "wb") as fh:
+    fh.write(b"not an npz")
+  rebuilt = graph_lib.cached_static_graph(cache_dir=str(tmp_path), **kw)
+  np.testing.assert_array_equal(rebuilt.m2g_senders, fresh.m2g_senders)
