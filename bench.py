@@ -360,10 +360,18 @@ def run_b200(args):
   # MACs the kernel really issues (the split edge layers execute fewer than the reference
   # dataflow the algorithmic figure is defined on), times the products per MAC.
   executed_tflops = (tc[1] / args.steps) * products / (tc_ms_per_step * 1e-3) / 1e12
+  # DRAM bytes of this kernel's launches in one step, from the committed ncu pass over the same
+  # build and workload (dram__bytes_read.sum + dram__bytes_write.sum, `profiles/r01_launches_v11_ncu.csv`:
+  # 110.9 GB read + 110.3 GB written; the algorithmic figure is 254.8 GB, the L2 absorbs part of
+  # the gathers).  Only meaningful for the configuration it was captured on.
+  traffic, traffic_src = None, None
+  if args.workload == DEFAULT_WORKLOAD and args.precision == "bf16x3" and args.pregather:
+    traffic, traffic_src = 221.2e9, "ncu, profiles/r01_launches_v11_ncu.csv"
   roofline = {
       "kernel": "gcb::mlp_layer_tc_kernel", "bound": "tensor",
       "achieved": achieved_tflops, "peak": peak_tf, "unit": "TFLOP/s",
-      "frac": achieved_tflops / peak_tf, "traffic": None, "peak_source": peak_src,
+      "frac": achieved_tflops / peak_tf, "traffic": traffic, "traffic_unit": "bytes per step (all launches of this kernel)",
+      "traffic_source": traffic_src, "peak_source": peak_src,
       "launches_per_step": tc[3] // args.steps, "kernel_ms_per_step": tc_ms_per_step,
       "kernel_share_of_step": tc_ms_per_step / (elapsed_ms / args.steps),
       "algorithmic_tflop_per_step": alg_flops / 1e12,
