@@ -39,3 +39,64 @@ for splits in range(0, 7):
       hashlib.sha256(s.tobytes() + r.tobytes()).digest(), np.uint8)
 np.savez_compressed(os.path.join(here, "icosahedral_mesh_reference.npz"), **out)
 print("wrote", os.path.join(here, "icosahedral_mesh_reference.npz"))
+
+
+# ---- checkpoint format (weathernext/utils/checkpoint.py is pure numpy and imports fine) ----
+# A GraphCast-CheckPoint-shaped tree (graphcast.py:115-151: params, model_config, task_config,
+# description, license) written by the REFERENCE's `checkpoint.dump`; the test loads it with
+# this repo's `checkpoint.load` into this repo's dataclasses and re-dumps it.
+import dataclasses  # noqa: E402
+from typing import Any, Optional  # noqa: E402
+
+from weathernext.utils import checkpoint as ref_ckpt  # noqa: E402
+
+
+@dataclasses.dataclass(frozen=True)
+class TaskConfig:
+  input_variables: tuple[str, ...]      # annotations as in weathernext/utils/task.py:21-28
+  target_variables: tuple[str, ...]
+  forcing_variables: tuple[str, ...]
+  pressure_levels: tuple[int, ...]
+  input_duration: str
+
+
+@dataclasses.dataclass(frozen=True)
+class ModelConfig:
+  resolution: float
+  mesh_size: int
+  latent_size: int
+  gnn_msg_steps: int
+  hidden_layers: int
+  radius_query_fraction_edge_length: float
+  mesh2grid_edge_normalization_factor: Optional[float] = None
+
+
+@dataclasses.dataclass(frozen=True)
+class CheckPoint:
+  params: dict[str, Any]
+  model_config: ModelConfig
+  task_config: TaskConfig
+  description: str
+  license: str
+
+
+rng = np.random.default_rng(5)
+ck = CheckPoint(
+    params={
+        "grid2mesh_gnn/~_networks_builder/encoder_nodes_grid_nodes_mlp/~/linear_0":
+            {"w": rng.standard_normal((7, 4)).astype(np.float32), "b": np.zeros(4, np.float32)},
+        "grid2mesh_gnn/~_networks_builder/encoder_nodes_grid_nodes_layer_norm":
+            {"scale": np.ones(4, np.float32), "offset": rng.standard_normal(4).astype(np.float32)},
+    },
+    model_config=ModelConfig(1.0, 5, 512, 16, 1, 0.6, None),
+    task_config=TaskConfig(("2m_temperature", "geopotential"), ("2m_temperature",),
+                           ("toa_incident_solar_radiation",), (50, 500, 1000), "12h"),
+    description="golden checkpoint written by the reference's checkpoint.dump",
+    license="n/a")
+path = os.path.join(here, "reference_checkpoint.npz")
+with open(path, "wb") as f:
+  ref_ckpt.dump(f, ck)
+with open(path, "rb") as f:                       # the reference reads its own file back
+  back = ref_ckpt.load(f, CheckPoint)
+assert back.model_config == ck.model_config and back.task_config == ck.task_config
+print("wrote", path)

@@ -119,3 +119,30 @@ def test_checkpoint_round_trip_and_format():
   buf = io.BytesIO(); checkpoint.dump(buf, cp); buf.seek(0)
   cp2 = checkpoint.load(buf, graphcast.CheckPoint)
   assert cp2.model_config == cp.model_config and cp2.task_config == cp.task_config
+
+
+def test_checkpoint_written_by_the_reference_loads_and_round_trips():
+  """tests/golden/reference_checkpoint.npz was written by the REFERENCE's
+  `weathernext.utils.checkpoint.dump` (tests/golden/make_golden.py).  This repo's loader must
+  read it into this repo's CheckPoint / ModelConfig / TaskConfig, and this repo's `dump` must
+  produce the same flat keys and values."""
+  import os
+  path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_checkpoint.npz")
+  with open(path, "rb") as f:
+    ck = checkpoint.load(f, graphcast.CheckPoint)
+  assert ck.model_config == graphcast.ModelConfig(1.0, 5, 512, 16, 1, 0.6, None)
+  assert ck.task_config == graphcast.TaskConfig(
+      input_variables=("2m_temperature", "geopotential"), target_variables=("2m_temperature",),
+      forcing_variables=("toa_incident_solar_radiation",), pressure_levels=(50, 500, 1000),
+      input_duration="12h")
+  assert ck.license == "n/a" and ck.description.startswith("golden checkpoint")
+  lin = ck.params["grid2mesh_gnn/~_networks_builder/encoder_nodes_grid_nodes_mlp/~/linear_0"]
+  assert lin["w"].shape == (7, 4) and lin["w"].dtype == np.float32 and not lin["b"].any()
+  ref = np.load(path)
+  buf = io.BytesIO()
+  checkpoint.dump(buf, ck)
+  buf.seek(0)
+  mine = np.load(buf)
+  assert set(mine.files) == set(ref.files)
+  for k in ref.files:
+    np.testing.assert_array_equal(mine[k], ref[k])
