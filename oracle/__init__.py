@@ -16,8 +16,17 @@ Pinning status:
     (icosahedral_mesh_test.py:36-94, grid_mesh_connectivity_test.py:23-47) and
     against golden vectors generated here by importing the reference's
     `icosahedral_mesh` module (tests/golden/, script tests/golden/make_golden.py).
-  * GNN forward (gather / MLP / LayerNorm / segment_sum / residuals), channel
-    packing, normalisation wrapper and rollout: PARITY UNPINNED -- the reference
+  * structural features (node features, receiver-local edge features of the three
+    graphs; `oracle/graph_features.py`) and the grid2mesh radius query: PINNED
+    against golden vectors computed by the reference's own numpy code
+    (`model_utils.py`, `legacy/grid_mesh_connectivity.py`, imported with jax /
+    xarray / trimesh stubbed out; tests/test_reference_geometry_golden.py).
+  * channel packing order and checkpoint format (product-side host logic):
+    PINNED against the reference's `dataset_to_stacked` / `stacked_to_dataset`
+    and `checkpoint.dump` (tests/golden/reference_packing.npz,
+    reference_checkpoint.npz).
+  * GNN forward (gather / MLP / LayerNorm / segment_sum / residuals; `oracle/gnn.py`),
+    normalisation wrapper and rollout: PARITY UNPINNED -- the reference
     has no test or golden vector for them and its JAX/haiku/jraph/xarray stack
     cannot be installed in this image (no network, not in /opt/wheelhouse), so
     these are restatements reviewed line by line against the cited code, not

@@ -100,3 +100,210 @@ with open(path, "rb") as f:                       # the reference reads its own 
   back = ref_ckpt.load(f, CheckPoint)
 assert back.model_config == ck.model_config and back.task_config == ck.task_config
 print("wrote", path)
+
+
+# ---- static-graph geometry and features, computed by the reference's own numpy code ----------
+# `weathernext/utils/model_utils.py` and `utils/legacy/grid_mesh_connectivity.py` import jax /
+# xarray / trimesh at module scope but the functions below are pure numpy + scipy.  The missing
+# packages are replaced by empty stub modules (attribute access yields dummy types, enough for
+# the annotations evaluated at import time); no reference code is modified or re-implemented.
+# Not reachable this way: `in_mesh_triangle_indices` (really calls trimesh) and everything that
+# touches xarray data.
+import types  # noqa: E402
+
+
+class _Stub(types.ModuleType):
+
+  def __getattr__(self, name):
+    if name.startswith("__"):
+      raise AttributeError(name)
+    return type(name, (), {})
+
+
+for _name in ("jax", "jax.numpy", "xarray", "xarray.ufuncs", "trimesh"):
+  sys.modules.setdefault(_name, _Stub(_name))
+sys.modules["jax"].numpy = sys.modules["jax.numpy"]
+sys.modules["xarray"].ufuncs = sys.modules["xarray.ufuncs"]
+
+from weathernext.utils import model_utils as ref_mu  # noqa: E402
+from weathernext.utils.legacy import grid_mesh_connectivity as ref_gm  # noqa: E402
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(here)))
+from graphcast_b200 import grid_mesh_connectivity as our_gm  # noqa: E402  (only for m2g INPUT indices)
+
+geo = {}
+lat = np.linspace(-90, 90, 19).astype(np.float32)     # float32 like GraphCast._init_grid_properties
+lon = np.arange(0, 360, 10.0).astype(np.float32)      # (graphcast.py:396-406)
+meshes = ref.get_hierarchy_of_triangular_meshes_for_sphere(2)
+finest = meshes[-1]
+geo["grid_lat"], geo["grid_lon"] = lat, lon
+geo["grid_coordinates"] = ref_gm._grid_lat_lon_to_coordinates(lat, lon)
+es, er = ref.faces_to_edges(finest.faces)
+max_edge = np.linalg.norm(finest.vertices[es] - finest.vertices[er], axis=-1).max()
+geo["radius"] = np.float64(0.6 * max_edge)
+g_idx, m_idx = ref_gm.radius_query_indices(grid_latitude=lat, grid_longitude=lon, mesh=finest,
+                                           radius=0.6 * max_edge)
+geo["g2m_grid_indices"], geo["g2m_mesh_indices"] = g_idx, m_idx
+phi, theta = ref_mu.cartesian_to_spherical(finest.vertices[:, 0], finest.vertices[:, 1],
+                                           finest.vertices[:, 2])
+mesh_lat, mesh_lon = ref_mu.spherical_to_lat_lon(phi=phi, theta=theta)
+geo["mesh_lat"], geo["mesh_lon"] = mesh_lat, mesh_lon
+lon2d, lat2d = np.meshgrid(lon, lat)
+glat, glon = lat2d.reshape(-1).astype(np.float32), lon2d.reshape(-1).astype(np.float32)
+kw = dict(add_node_positions=False, add_node_latitude=True, add_node_longitude=True,
+          add_relative_positions=True, relative_longitude_local_coordinates=True,
+          relative_latitude_local_coordinates=True)      # graphcast.py:408-548 call sites
+sn, rn, ef = ref_mu.get_bipartite_graph_spatial_features(
+    senders_node_lat=glat, senders_node_lon=glon,
+    receivers_node_lat=mesh_lat.astype(np.float32), receivers_node_lon=mesh_lon.astype(np.float32),
+    senders=g_idx, receivers=m_idx, edge_normalization_factor=None, **kw)
+geo["g2m_grid_node_feats"], geo["g2m_mesh_node_feats"], geo["g2m_edge_feats"] = sn, rn, ef
+merged = ref.merge_meshes(meshes)
+ms, mr = ref.faces_to_edges(merged.faces)
+nf, mef = ref_mu.get_graph_spatial_features(
+    node_lat=mesh_lat.astype(np.float32), node_lon=mesh_lon.astype(np.float32),
+    senders=ms, receivers=mr, **kw)
+geo["mesh_node_feats"], geo["mesh_edge_feats"] = nf, mef
+geo["mesh_senders"], geo["mesh_receivers"] = ms, mr
+# mesh2grid: the containing-triangle lookup itself needs trimesh; the edge FEATURES for a given
+# index list do not.  The indices are an input of this golden (stored), the features the output.
+g3, m3 = our_gm.in_mesh_triangle_indices(grid_latitude=lat, grid_longitude=lon, mesh=finest)
+geo["m2g_grid_indices"], geo["m2g_mesh_indices"] = g3, m3
+for tag, norm in (("", None), ("_norm2", 2.0)):
+  _, _, ef3 = ref_mu.get_bipartite_graph_spatial_features(
+      senders_node_lat=mesh_lat.astype(np.float32), senders_node_lon=mesh_lon.astype(np.float32),
+      receivers_node_lat=glat, receivers_node_lon=glon, senders=m3, receivers=g3,
+      edge_normalization_factor=norm, **kw)
+  geo["m2g_edge_feats" + tag] = ef3
+np.savez_compressed(os.path.join(here, "reference_geometry.npz"), **geo)
+print("wrote", os.path.join(here, "reference_geometry.npz"),
+      {k: (v.shape, str(v.dtype)) for k, v in geo.items() if hasattr(v, "shape")})
+
+
+# ---- channel packing: the reference's dataset_to_stacked / stacked_to_dataset ----------------
+# These functions (model_utils.py:645-776) decide the channel ORDER of the model's inputs and
+# outputs: variables sorted by name, non-(batch, lat, lon) dims stacked in the variable's own dim
+# order.  They only use a small part of the xarray API, which is provided below by a numpy-backed
+# stand-in following xarray's documented semantics (Variable.stack: stacked dims moved to the
+# end and flattened in C order, first listed dim slowest; set_dims: broadcast to the requested
+# dims, in the requested order; unstack: the inverse reshape).  The reference code itself runs
+# unmodified on top of it.
+class _Sizes(dict):
+  pass
+
+
+class FakeVariable:
+
+  def __init__(self, dims, data):
+    self.dims = tuple(dims)
+    self.data = np.asarray(data)
+    assert self.data.ndim == len(self.dims)
+
+  @property
+  def sizes(self):
+    return _Sizes(zip(self.dims, self.data.shape))
+
+  def transpose(self, *dims):
+    return FakeVariable(dims, np.transpose(self.data, [self.dims.index(d) for d in dims]))
+
+  def stack(self, **kw):
+    (new_dim, stacked), = kw.items()
+    keep = [d for d in self.dims if d not in stacked]
+    v = self.transpose(*keep, *stacked)
+    shape = v.data.shape[:len(keep)] + (-1,)
+    return FakeVariable(tuple(keep) + (new_dim,), v.data.reshape(shape))
+
+  def unstack(self, mapping):
+    (old_dim, sizes), = mapping.items()
+    assert self.dims[-1] == old_dim
+    new_dims = self.dims[:-1] + tuple(sizes.keys())
+    return FakeVariable(new_dims, self.data.reshape(self.data.shape[:-1] + tuple(sizes.values())))
+
+  def set_dims(self, dims):
+    names = list(dims.keys())
+    missing = [d for d in names if d not in self.dims]
+    data = self.data.reshape((1,) * len(missing) + self.data.shape)
+    v = FakeVariable(tuple(missing) + self.dims, data).transpose(*names)
+    return FakeVariable(names, np.broadcast_to(v.data, [dims[d] for d in names]))
+
+  def isel(self, indexers):
+    idx = tuple(indexers.get(d, slice(None)) for d in self.dims)
+    return FakeVariable(self.dims, self.data[idx])
+
+  @staticmethod
+  def concat(variables, dim):
+    axis = variables[0].dims.index(dim)
+    return FakeVariable(variables[0].dims, np.concatenate([v.data for v in variables], axis=axis))
+
+
+class FakeDataArray(FakeVariable):
+
+  def __init__(self, data, coords=None, dims=None, name=None):
+    if isinstance(data, FakeVariable):
+      dims, data = data.dims, data.data
+    super().__init__(dims, data)
+    self.coords = dict(coords or {})
+    self.name = name
+
+
+class FakeDataset(dict):
+
+  def __init__(self, data_vars, coords=None):
+    super().__init__(data_vars)
+    self.coords = dict(coords or {})
+
+  @property
+  def data_vars(self):
+    return self
+
+  @property
+  def variables(self):
+    return self
+
+  @property
+  def sizes(self):
+    out = {}
+    for v in self.values():
+      out.update(v.sizes)
+    return out
+
+
+ref_mu.xr.Variable = FakeVariable
+ref_mu.xr.DataArray = FakeDataArray
+ref_mu.xr.Dataset = FakeDataset
+
+B, T, L, LA, LO = 2, 2, 3, 4, 5
+rng = np.random.default_rng(9)
+mk = lambda *shape: rng.standard_normal(shape).astype(np.float32)
+inputs_np = {
+    "2m_temperature": (("batch", "time", "lat", "lon"), mk(B, T, LA, LO)),
+    "geopotential": (("batch", "time", "level", "lat", "lon"), mk(B, T, L, LA, LO)),
+    "land_sea_mask": (("lat", "lon"), mk(LA, LO)),                       # static: broadcast over batch
+    "toa_incident_solar_radiation": (("batch", "time", "lat", "lon"), mk(B, T, LA, LO)),
+    "10m_u_component_of_wind": (("batch", "time", "lat", "lon"), mk(B, T, LA, LO)),
+}
+ds = FakeDataset({k: FakeDataArray(v, dims=d, name=k) for k, (d, v) in inputs_np.items()})
+stacked = ref_mu.dataset_to_stacked(ds)
+assert stacked.dims == ("batch", "lat", "lon", "channels")
+pack = {"stacked_inputs": stacked.data}
+for k, (d, v) in inputs_np.items():
+  pack["in:" + k] = v
+  pack["in_dims:" + k] = np.array(d)
+template_np = {
+    "2m_temperature": (("batch", "time", "lat", "lon"), (B, 1, LA, LO)),
+    "geopotential": (("batch", "time", "level", "lat", "lon"), (B, 1, L, LA, LO)),
+    "total_precipitation_6hr": (("batch", "time", "lat", "lon"), (B, 1, LA, LO)),
+}
+tmpl = FakeDataset({k: FakeDataArray(np.zeros(shape, np.float32), dims=d, name=k)
+                    for k, (d, shape) in template_np.items()})
+n_out = sum(int(np.prod([s for dd, s in zip(d, shape) if dd not in ("batch", "lat", "lon")]))
+            for d, shape in template_np.values())
+flat = rng.standard_normal((B, LA, LO, n_out)).astype(np.float32)
+out_ds = ref_mu.stacked_to_dataset(FakeVariable(("batch", "lat", "lon", "channels"), flat), tmpl)
+pack["stacked_outputs"] = flat
+for k, (d, shape) in template_np.items():
+  assert out_ds[k].dims == d
+  pack["out:" + k] = out_ds[k].data
+  pack["out_dims:" + k] = np.array(d)
+np.savez_compressed(os.path.join(here, "reference_packing.npz"), **pack)
+print("wrote", os.path.join(here, "reference_packing.npz"), stacked.data.shape, n_out)
