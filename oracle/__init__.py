@@ -25,10 +25,14 @@ Pinning status:
     PINNED against the reference's `dataset_to_stacked` / `stacked_to_dataset`
     and `checkpoint.dump` (tests/golden/reference_packing.npz,
     reference_checkpoint.npz).
-  * GNN forward (gather / MLP / LayerNorm / segment_sum / residuals; `oracle/gnn.py`),
-    normalisation wrapper and rollout: PARITY UNPINNED -- the reference
-    has no test or golden vector for them and its JAX/haiku/jraph/xarray stack
-    cannot be installed in this image (no network, not in /opt/wheelhouse), so
-    these are restatements reviewed line by line against the cited code, not
-    outputs of the executed reference.
+  * GNN forward (`oracle/gnn.py`): PINNED against the reference's own wiring, executed:
+    tests/golden/make_golden.py imports and runs weathernext1_graph/graphcast.py
+    (`_maybe_init`, `_run_grid2mesh_gnn`, `_run_mesh_gnn`, `_run_mesh2grid_gnn`),
+    legacy/deep_typed_graph_net.py and typed_graph_net.py on numpy stand-ins for jax / jraph /
+    haiku / chex (tests/golden/numpy_standins.py); the oracle reproduces its outputs and
+    intermediate latents to 5.5e-7 (tests/test_reference_gnn_golden.py).  Only the third-party
+    primitives (Linear, LayerNorm, swish, segment_sum, concatenated_args) are restated there.
+  * normalisation wrapper and rollout next-input assembly: PARITY UNPINNED -- xarray programs
+    for which the reference has no test or golden vector and whose stack cannot be installed
+    in this image; restatements reviewed line by line against the cited code.
 """

@@ -307,3 +307,59 @@ for k, (d, shape) in template_np.items():
   pack["out_dims:" + k] = np.array(d)
 np.savez_compressed(os.path.join(here, "reference_packing.npz"), **pack)
 print("wrote", os.path.join(here, "reference_packing.npz"), stacked.data.shape, n_out)
+
+
+# ---- the GNN forward: the reference's GraphCast wiring executed on numpy stand-ins -----------
+# weathernext1_graph/graphcast.py, utils/legacy/deep_typed_graph_net.py and utils/typed_graph_net.py
+# are imported and RUN (graph construction, `_run_grid2mesh_gnn`, `_run_mesh_gnn`,
+# `_run_mesh2grid_gnn`: concat orders, gathers, per-receiver aggregation, residuals, which node
+# set is updated when, the three-GNN composition) with jax / jraph / haiku / chex replaced by
+# the few numpy primitives of tests/golden/numpy_standins.py.  Only `in_mesh_triangle_indices`
+# (needs trimesh) is taken from this repo; the xarray I/O of `__call__` is bypassed by calling
+# the three `_run_*` methods on a raw [Ng, B, C] array.
+import numpy_standins as ns  # noqa: E402
+
+ns.install()
+from weathernext.weathernext1_graph import graphcast as ref_gc  # noqa: E402
+from weathernext.utils.legacy import grid_mesh_connectivity as ref_gm2  # noqa: E402
+
+ref_gm2.in_mesh_triangle_indices = our_gm.in_mesh_triangle_indices
+task = ref_gc.TaskConfig(
+    input_variables=("2m_temperature", "geopotential", "toa_incident_solar_radiation"),
+    target_variables=("2m_temperature", "geopotential"),
+    forcing_variables=("toa_incident_solar_radiation",), pressure_levels=(500, 850),
+    input_duration="12h")
+cfg = ref_gc.ModelConfig(resolution=10.0, mesh_size=2, latent_size=32, gnn_msg_steps=3,
+                         hidden_layers=1, radius_query_fraction_edge_length=0.6)
+model = ref_gc.GraphCast(cfg, task)
+glat = np.linspace(-90, 90, 19).astype(np.float32)
+glon = np.arange(0, 360, 10.0).astype(np.float32)
+model._maybe_init(types.SimpleNamespace(lat=glat, lon=glon))
+x = np.random.default_rng(0).standard_normal((19 * 36, 2, 7)).astype(np.float32)
+latent_mesh, latent_grid = model._run_grid2mesh_gnn(x)
+updated_mesh = model._run_mesh_gnn(latent_mesh)
+output = model._run_mesh2grid_gnn(updated_mesh, latent_grid)
+gnn = {"grid_lat": glat, "grid_lon": glon, "grid_features": x,
+       "latent_mesh_after_grid2mesh": latent_mesh, "latent_grid_after_grid2mesh": latent_grid,
+       "latent_mesh_after_mesh_gnn": updated_mesh, "output": output,
+       "mesh_size": np.int64(2), "gnn_msg_steps": np.int64(3)}
+
+
+def _edges(graph, name):
+  key = graph.edge_key_by_name(name)
+  es = graph.edges[key]
+  return es.indices.senders, es.indices.receivers, es.features
+
+
+g2m, mesh_g, m2g = (model._grid2mesh_graph_structure, model._mesh_graph_structure,
+                    model._mesh2grid_graph_structure)
+gnn["grid_node_feats"] = g2m.nodes["grid_nodes"].features
+gnn["mesh_node_feats"] = g2m.nodes["mesh_nodes"].features
+for tag, graph, name in (("g2m", g2m, "grid2mesh"), ("mesh", mesh_g, "mesh"), ("m2g", m2g, "mesh2grid")):
+  s_, r_, f_ = _edges(graph, name)
+  gnn[f"{tag}_senders"], gnn[f"{tag}_receivers"], gnn[f"{tag}_edge_feats"] = s_, r_, f_
+for path, entry in ns.PARAMS.items():
+  for leaf, value in entry.items():
+    gnn[f"param:{path}:{leaf}"] = value
+np.savez_compressed(os.path.join(here, "reference_gnn_forward.npz"), **gnn)
+print("wrote", os.path.join(here, "reference_gnn_forward.npz"), output.shape, len(ns.PARAMS), "param entries")
