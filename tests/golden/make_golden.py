@@ -204,7 +204,16 @@ class FakeVariable:
     return _Sizes(zip(self.dims, self.data.shape))
 
   def transpose(self, *dims):
+    if Ellipsis in dims:                              # transpose("lat", "lon", ...)
+      named = [d for d in dims if d is not Ellipsis]
+      rest = [d for d in self.dims if d not in named]
+      i = dims.index(Ellipsis)
+      dims = tuple(dims[:i]) + tuple(rest) + tuple(dims[i + 1:])
     return FakeVariable(dims, np.transpose(self.data, [self.dims.index(d) for d in dims]))
+
+  @property
+  def variable(self):
+    return self
 
   def stack(self, **kw):
     (new_dim, stacked), = kw.items()
@@ -335,10 +344,33 @@ model = ref_gc.GraphCast(cfg, task)
 glat = np.linspace(-90, 90, 19).astype(np.float32)
 glon = np.arange(0, 360, 10.0).astype(np.float32)
 model._maybe_init(types.SimpleNamespace(lat=glat, lon=glon))
-x = np.random.default_rng(0).standard_normal((19 * 36, 2, 7)).astype(np.float32)
+# Inputs as (stand-in) xarray datasets, converted by the reference's own
+# `_inputs_to_grid_node_features` (graphcast.py:680-699); the full `__call__` is run below.
+ref_gc.xarray.concat = lambda arrays, dim: FakeDataArray(FakeVariable.concat(list(arrays), dim))
+ref_gc.xarray_jax.unwrap = lambda v: v
+ref_gc.xarray_jax.DataArray = lambda data, dims: FakeDataArray(data, dims=dims)
+NB, NLAT, NLON = 2, 19, 36
+rng = np.random.default_rng(0)
+mk = lambda *shape: rng.standard_normal(shape).astype(np.float32)
+api_inputs = {
+    "2m_temperature": (("batch", "time", "lat", "lon"), mk(NB, 2, NLAT, NLON)),
+    "geopotential": (("batch", "time", "level", "lat", "lon"), mk(NB, 2, 2, NLAT, NLON)),
+    "toa_incident_solar_radiation": (("batch", "time", "lat", "lon"), mk(NB, 2, NLAT, NLON)),
+}
+api_forcings = {"toa_incident_solar_radiation": (("batch", "time", "lat", "lon"), mk(NB, 1, NLAT, NLON))}
+api_template = {
+    "2m_temperature": (("batch", "time", "lat", "lon"), np.zeros((NB, 1, NLAT, NLON), np.float32)),
+    "geopotential": (("batch", "time", "level", "lat", "lon"), np.zeros((NB, 1, 2, NLAT, NLON), np.float32)),
+}
+to_ds = lambda spec: FakeDataset({k: FakeDataArray(v, dims=d, name=k) for k, (d, v) in spec.items()})
+ds_inputs, ds_forcings, ds_template = to_ds(api_inputs), to_ds(api_forcings), to_ds(api_template)
+ds_inputs.lat, ds_inputs.lon = glat, glon
+x = model._inputs_to_grid_node_features(ds_inputs, ds_forcings)
+assert x.shape == (NLAT * NLON, NB, 9)
 latent_mesh, latent_grid = model._run_grid2mesh_gnn(x)
 updated_mesh = model._run_mesh_gnn(latent_mesh)
 output = model._run_mesh2grid_gnn(updated_mesh, latent_grid)
+predictions = model(ds_inputs, ds_template, ds_forcings)          # the reference's __call__, end to end
 gnn = {"grid_lat": glat, "grid_lon": glon, "grid_features": x,
        "latent_mesh_after_grid2mesh": latent_mesh, "latent_grid_after_grid2mesh": latent_grid,
        "latent_mesh_after_mesh_gnn": updated_mesh, "output": output,
@@ -358,6 +390,12 @@ gnn["mesh_node_feats"] = g2m.nodes["mesh_nodes"].features
 for tag, graph, name in (("g2m", g2m, "grid2mesh"), ("mesh", mesh_g, "mesh"), ("m2g", m2g, "mesh2grid")):
   s_, r_, f_ = _edges(graph, name)
   gnn[f"{tag}_senders"], gnn[f"{tag}_receivers"], gnn[f"{tag}_edge_feats"] = s_, r_, f_
+for tag, spec in (("api_in", api_inputs), ("api_forcing", api_forcings)):
+  for k, (d, v) in spec.items():
+    gnn[f"{tag}:{k}"], gnn[f"{tag}_dims:{k}"] = v, np.array(d)
+for k, (d, v) in api_template.items():
+  assert predictions[k].dims == d
+  gnn[f"api_out:{k}"], gnn[f"api_out_dims:{k}"] = predictions[k].data, np.array(d)
 for path, entry in ns.PARAMS.items():
   for leaf, value in entry.items():
     gnn[f"param:{path}:{leaf}"] = value

@@ -126,7 +126,8 @@ def _repeat(a, repeats, axis=None, total_repeat_length=None):
 
 
 def _swish(x):
-  return x / (1.0 + np.exp(-x))          # x * sigmoid(x)
+  with np.errstate(over="ignore"):       # exp(-x) -> inf for very negative x: x / inf = -0, as wanted
+    return x / (1.0 + np.exp(-x))        # x * sigmoid(x)
 
 
 def _make_jax():

@@ -92,3 +92,41 @@ def test_oracle_on_this_repos_static_graph_matches_executed_reference(ref):
   orc = oracle_gnn.Oracle(_params(ref), torch.float32)
   out = orc.forward(g.as_dict(), ref["grid_features"])
   assert _rel(out.numpy(), ref["output"]) < 5e-5
+
+
+def _api_dataset(ref, prefix):
+  from graphcast_b200 import xarray_shim as xs
+  names = [k[len(prefix) + 1:] for k in ref if k.startswith(prefix + ":")]
+  return xs.Dataset({n: (tuple(str(d) for d in ref[f"{prefix}_dims:{n}"]), ref[f"{prefix}:{n}"])
+                     for n in names})
+
+
+def test_inputs_to_grid_node_features_matches_executed_reference(ref):
+  """[Ng, B, C] assembly of `GraphCast._inputs_to_grid_node_features` (graphcast.py:680-699):
+  inputs then forcings on the channel axis, node = lat * n_lon + lon."""
+  from graphcast_b200 import model_utils
+  inputs, forcings = _api_dataset(ref, "api_in"), _api_dataset(ref, "api_forcing")
+  stacked = np.concatenate([model_utils.dataset_to_stacked(inputs),
+                            model_utils.dataset_to_stacked(forcings, inputs.sizes)], -1)
+  b, la, lo, c = stacked.shape
+  x = np.transpose(stacked, (1, 2, 0, 3)).reshape(la * lo, b, c)
+  np.testing.assert_array_equal(x, ref["grid_features"])
+
+
+def test_api_level_oracle_matches_the_reference_call(ref):
+  """The helper that gates the GPU `GraphCast.__call__` test (tests/test_gpu_model.py:
+  `_oracle_for_api`) against the reference's own `GraphCast.__call__`, executed end to end on
+  stand-in datasets: Dataset -> features -> three GNNs -> Dataset."""
+  import dataclasses
+  import test_gpu_model
+  from graphcast_b200 import model_utils
+  inputs, forcings = _api_dataset(ref, "api_in"), _api_dataset(ref, "api_forcing")
+  template = _api_dataset(ref, "api_out")
+  g = dataclasses.make_dataclass("G", ["d"])(_graph_from_reference(ref))
+  g.as_dict = lambda: g.d
+  y = test_gpu_model._oracle_for_api(None, None, inputs, forcings, _params(ref), g)   # [B, lat, lon, n_out]
+  got = model_utils.stacked_to_dataset(y, template)
+  for name in template.data_vars.keys():
+    want = ref[f"api_out:{name}"]
+    assert got[name].dims == tuple(str(d) for d in ref[f"api_out_dims:{name}"])
+    assert _rel(np.asarray(got[name].data), want) < 2e-5
