@@ -401,3 +401,103 @@ for path, entry in ns.PARAMS.items():
     gnn[f"param:{path}:{leaf}"] = value
 np.savez_compressed(os.path.join(here, "reference_gnn_forward.npz"), **gnn)
 print("wrote", os.path.join(here, "reference_gnn_forward.npz"), output.shape, len(ns.PARAMS), "param entries")
+
+
+# ---- normalisation wrapper: the reference's InputsAndResiduals.__call__ executed ---------------
+# utils/normalization.py and utils/xarray_tree.py run unmodified on the stand-in datasets, which
+# get the remaining xarray behaviour they need: arithmetic that broadcasts by dimension NAME
+# (result dims = dims of the left operand, then the new dims of the right one), `astype`,
+# `isel(time=-1)` (an integer index drops the dim), `rename`, `merge`.
+def _binary(a, b, op):
+  if not isinstance(b, FakeVariable):
+    return FakeDataArray(op(a.data, b), dims=a.dims, name=getattr(a, "name", None))
+  dims = tuple(a.dims) + tuple(d for d in b.dims if d not in a.dims)
+
+  def expand(v):
+    have = [d for d in dims if d in v.dims]
+    data = np.transpose(v.data, [v.dims.index(d) for d in have])
+    return data.reshape([v.sizes[d] if d in v.dims else 1 for d in dims])
+
+  return FakeDataArray(op(expand(a), expand(b)), dims=dims, name=getattr(a, "name", None))
+
+
+FakeVariable.__sub__ = lambda a, b: _binary(a, b, np.subtract)
+FakeVariable.__add__ = lambda a, b: _binary(a, b, np.add)
+FakeVariable.__mul__ = lambda a, b: _binary(a, b, np.multiply)
+FakeVariable.__truediv__ = lambda a, b: _binary(a, b, np.divide)
+FakeVariable.dtype = property(lambda self: self.data.dtype)
+FakeVariable.astype = lambda self, dt: FakeDataArray(self.data.astype(dt), dims=self.dims,
+                                                     name=getattr(self, "name", None))
+FakeDataArray.rename = lambda self, name: FakeDataArray(self.data, dims=self.dims, name=name)
+_isel_dict = FakeVariable.isel
+
+
+def _isel(self, indexers=None, **kw):
+  indexers = dict(indexers or {}, **kw)
+  out = _isel_dict(self, {k: v for k, v in indexers.items() if isinstance(v, slice)})
+  for k, v in indexers.items():
+    if not isinstance(v, slice):                        # integer: index and drop the dim
+      ax = out.dims.index(k)
+      out = FakeVariable(out.dims[:ax] + out.dims[ax + 1:], np.take(out.data, v, axis=ax))
+  return FakeDataArray(out.data, dims=out.dims, name=getattr(self, "name", None))
+
+
+FakeVariable.isel = _isel
+import importlib  # noqa: E402
+
+xr_mod = sys.modules["xarray"]
+xr_mod.Dataset, xr_mod.DataArray = FakeDataset, FakeDataArray
+xr_mod.merge = lambda arrays, join=None, compat=None: FakeDataset({a.name: a for a in arrays})
+ref_norm = importlib.import_module("weathernext.utils.normalization")
+
+levels = 2
+stats_spec = lambda fn: FakeDataset({
+    "2m_temperature": FakeDataArray(np.float32(fn(0)), dims=(), name="2m_temperature"),
+    "geopotential": FakeDataArray(np.array([fn(1), fn(2)], np.float32), dims=("level",), name="geopotential"),
+    "toa_incident_solar_radiation": FakeDataArray(np.float32(fn(3)), dims=(), name="toa_incident_solar_radiation"),
+    "total_precipitation_6hr": FakeDataArray(np.float32(fn(4)), dims=(), name="total_precipitation_6hr"),
+})
+mean_by_level = stats_spec(lambda i: 1.5 * i - 2.0)
+stddev_by_level = stats_spec(lambda i: 0.5 + 0.75 * i)
+diffs_stddev_by_level = stats_spec(lambda i: 0.1 + 0.05 * i)
+captured = {}
+
+
+def inner_predictor(norm_inputs, targets_template, forcings):
+  """Stands for the model: records what it is given, returns a fixed function of it."""
+  captured["norm_inputs"], captured["norm_forcings"] = norm_inputs, forcings
+  out = {}
+  for name in targets_template.keys():
+    if name in norm_inputs.keys():
+      v = norm_inputs[name]
+      out[name] = FakeDataArray(0.5 * v.data[:, -1:] + 0.25, dims=v.dims, name=name)
+    else:                                                   # target-only variable
+      t = targets_template[name]
+      out[name] = FakeDataArray(np.full(t.data.shape, 0.125, np.float32) * (1 + np.arange(t.data.shape[-1], dtype=np.float32)),
+                                dims=t.dims, name=name)
+  return FakeDataset(out)
+
+
+norm_template = dict(api_template)
+norm_template["total_precipitation_6hr"] = (("batch", "time", "lat", "lon"), np.zeros((NB, 1, NLAT, NLON), np.float32))
+wrapped = ref_norm.InputsAndResiduals(inner_predictor, stddev_by_level=stddev_by_level,
+                                      mean_by_level=mean_by_level,
+                                      diffs_stddev_by_level=diffs_stddev_by_level)
+norm_out = wrapped(ds_inputs, to_ds(norm_template), ds_forcings)
+nz = {}
+for tag, spec in (("in", api_inputs), ("forcing", api_forcings)):
+  for k, (d, v) in spec.items():
+    nz[f"{tag}:{k}"], nz[f"{tag}_dims:{k}"] = v, np.array(d)
+for k, (d, v) in norm_template.items():
+  nz[f"template_dims:{k}"], nz[f"template_shape:{k}"] = np.array(d), np.array(v.shape)
+for sname, sds in (("mean", mean_by_level), ("std", stddev_by_level), ("diffs_std", diffs_stddev_by_level)):
+  for k in sds.keys():
+    nz[f"{sname}:{k}"], nz[f"{sname}_dims:{k}"] = sds[k].data, np.array(sds[k].dims, dtype=str)
+for k in captured["norm_inputs"].keys():
+  nz[f"norm_in:{k}"] = captured["norm_inputs"][k].data
+for k in captured["norm_forcings"].keys():
+  nz[f"norm_forcing:{k}"] = captured["norm_forcings"][k].data
+for k in norm_out.keys():
+  nz[f"out:{k}"], nz[f"out_dims:{k}"] = norm_out[k].data, np.array(norm_out[k].dims)
+np.savez_compressed(os.path.join(here, "reference_normalization.npz"), **nz)
+print("wrote", os.path.join(here, "reference_normalization.npz"), sorted(norm_out.keys()))
