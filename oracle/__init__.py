@@ -32,7 +32,11 @@ Pinning status:
     haiku / chex (tests/golden/numpy_standins.py); the oracle reproduces its outputs and
     intermediate latents to 5.5e-7 (tests/test_reference_gnn_golden.py).  Only the third-party
     primitives (Linear, LayerNorm, swish, segment_sum, concatenated_args) are restated there.
-  * normalisation wrapper and rollout next-input assembly: PARITY UNPINNED -- xarray programs
-    for which the reference has no test or golden vector and whose stack cannot be installed
-    in this image; restatements reviewed line by line against the cited code.
+  * `GraphCast.__call__` I/O conversion, normalisation wrapper (`InputsAndResiduals`) and
+    rollout (`chunked_prediction_generator`, `_get_next_inputs`): the product's host logic is
+    PINNED the same way -- the reference functions are executed on numpy-backed stand-in
+    datasets (tests/golden/reference_{gnn_forward,normalization,rollout}.npz).
+  * Not exercised anywhere: the real jax / haiku / jraph / xarray packages (not installable in
+    this image).  The stand-ins restate only the primitives the executed reference code calls;
+    they are listed at the top of tests/golden/numpy_standins.py and make_golden.py.
 """

@@ -501,3 +501,135 @@ for k in norm_out.keys():
   nz[f"out:{k}"], nz[f"out_dims:{k}"] = norm_out[k].data, np.array(norm_out[k].dims)
 np.savez_compressed(os.path.join(here, "reference_normalization.npz"), **nz)
 print("wrote", os.path.join(here, "reference_normalization.npz"), sorted(norm_out.keys()))
+
+
+# ---- rollout: the reference's chunked_prediction_generator / _get_next_inputs executed ----------
+# utils/rollout.py runs unmodified.  Its xarray use needs a dataset with coordinates: `RDataset`
+# below adds `coords` (name -> DataArray), `copy`, `isel(time=slice)` (data and time coordinates),
+# `assign_coords`, `assign`, `compute`, `__getitem__(list)`, `dims`, and `xarray.concat(...,
+# dim="time", data_vars="different")` + `tail` as used by `_get_next_inputs` (variables without
+# the concat dim are taken from the first dataset).  jax.jit / vmap / random.split are identity
+# functions here (no randomness is used by the recording predictor).
+class RDataset(FakeDataset):
+
+  def __init__(self, data_vars, coords=None):
+    super().__init__(data_vars, coords)
+
+  def copy(self):
+    return RDataset(dict(self), dict(self.coords))
+
+  def compute(self):
+    return self
+
+  def __getitem__(self, key):
+    if isinstance(key, list):
+      return RDataset({k: dict.__getitem__(self, k) for k in key}, dict(self.coords))
+    return dict.__getitem__(self, key)
+
+  @property
+  def dims(self):
+    out = []
+    for v in self.values():
+      out.extend(d for d in v.dims if d not in out)
+    return tuple(out)
+
+  def isel(self, **kw):
+    data = {k: (v.isel(kw) if all(d in v.dims for d in kw) else v) for k, v in self.items()}
+    coords = {k: (c.isel(kw) if all(d in c.dims for d in kw) else c) for k, c in self.coords.items()}
+    return RDataset(data, coords)
+
+  def assign_coords(self, coords=None, **kw):
+    new = dict(self.coords)
+    for k, v in dict(coords or {}, **kw).items():
+      new[k] = v if isinstance(v, FakeVariable) else FakeDataArray(np.asarray(v), dims=(k,), name=k)
+    return RDataset(dict(self), new)
+
+  def assign(self, other):
+    data = dict(self)
+    data.update(other)
+    return RDataset(data, dict(self.coords))
+
+  def tail(self, **kw):
+    (dim, n), = kw.items()
+    return self.isel(**{dim: slice(-n, None)})
+
+
+def _concat(datasets, dim, data_vars=None, compat=None):
+  first = datasets[0]
+  out = {}
+  for k, v in first.items():
+    if dim in v.dims:
+      parts = [ds[k].transpose(*v.dims) for ds in datasets]
+      out[k] = FakeDataArray(FakeVariable.concat(parts, dim), name=k)
+    else:
+      out[k] = v                                            # data_vars="different": not concatenated
+  coords = dict(first.coords)
+  if dim in coords:
+    coords[dim] = FakeDataArray(np.concatenate([ds.coords[dim].data for ds in datasets]), dims=(dim,), name=dim)
+  return RDataset(out, coords)
+
+
+jax_mod = sys.modules["jax"]
+jax_mod.jit = lambda f, **kw: f
+jax_mod.vmap = lambda f, **kw: f
+jax_mod.pmap = lambda f, **kw: f
+jax_mod.random = types.SimpleNamespace(split=lambda rng: (rng, rng))
+xr_mod.Dataset = RDataset
+xr_mod.concat = _concat
+ref_rollout = importlib.import_module("weathernext.utils.rollout")
+
+NSTEPS = 4
+hour = np.timedelta64(6, "h")
+roll_inputs_np = {
+    "2m_temperature": (("batch", "time", "lat", "lon"), mk(NB, 2, 3, 4)),
+    "geopotential": (("batch", "time", "level", "lat", "lon"), mk(NB, 2, 2, 3, 4)),
+    "toa_incident_solar_radiation": (("batch", "time", "lat", "lon"), mk(NB, 2, 3, 4)),
+    "land_sea_mask": (("lat", "lon"), mk(3, 4)),
+}
+roll_forcings_np = {"toa_incident_solar_radiation": (("batch", "time", "lat", "lon"), mk(NB, NSTEPS, 3, 4))}
+roll_template_np = {
+    "2m_temperature": (("batch", "time", "lat", "lon"), np.zeros((NB, NSTEPS, 3, 4), np.float32)),
+    "geopotential": (("batch", "time", "level", "lat", "lon"), np.zeros((NB, NSTEPS, 2, 3, 4), np.float32)),
+}
+time_coord = lambda values: {"time": FakeDataArray(np.asarray(values), dims=("time",), name="time")}
+to_rds = lambda spec, times: RDataset({k: FakeDataArray(v, dims=d, name=k) for k, (d, v) in spec.items()},
+                                      time_coord(times))
+in_times = np.array([-1, 0]) * hour
+tgt_times = (np.arange(NSTEPS) + 1) * hour
+calls = []
+
+
+def recording_predictor(rng, inputs, targets_template, forcings):
+  """Depends on both input frames and on the forcing of the target time, so that the order of
+  the frames and the forcing slice fed at every step show up in the trajectory."""
+  calls.append({"in_time": inputs.coords["time"].data.copy(),
+                "target_time": targets_template.coords["time"].data.copy()})
+  f = forcings["toa_incident_solar_radiation"].data                 # [B, 1, lat, lon]
+  out = {}
+  for name in targets_template.keys():
+    x = inputs[name].data                                            # [B, 2, ...]
+    fb = f.reshape(f.shape[:2] + (1,) * (x.ndim - 4) + f.shape[2:])
+    out[name] = FakeDataArray(0.9 * x[:, 1:] + 0.1 * x[:, :1] + 0.05 * fb + 0.01 * inputs["land_sea_mask"].data,
+                              dims=inputs[name].dims, name=name)
+  return RDataset(out, dict(targets_template.coords))
+
+
+chunks = list(ref_rollout.chunked_prediction_generator(
+    recording_predictor, rng=0, inputs=to_rds(roll_inputs_np, in_times),
+    targets_template=to_rds(roll_template_np, tgt_times), num_steps_per_chunk=1,
+    forcings=to_rds(roll_forcings_np, tgt_times)))
+assert len(chunks) == NSTEPS
+ro = {"in_times": in_times.astype("timedelta64[h]").astype(np.int64),
+      "target_times": tgt_times.astype("timedelta64[h]").astype(np.int64)}
+for tag, spec in (("in", roll_inputs_np), ("forcing", roll_forcings_np), ("template", roll_template_np)):
+  for k, (d, v) in spec.items():
+    ro[f"{tag}:{k}"], ro[f"{tag}_dims:{k}"] = v, np.array(d)
+for i, (chunk, call) in enumerate(zip(chunks, calls)):
+  for k in chunk.keys():
+    ro[f"chunk{i}:{k}"] = chunk[k].data
+  ro[f"chunk{i}_time"] = chunk.coords["time"].data.astype("timedelta64[h]").astype(np.int64)
+  ro[f"call{i}_in_time"] = call["in_time"].astype("timedelta64[h]").astype(np.int64)
+  ro[f"call{i}_target_time"] = call["target_time"].astype("timedelta64[h]").astype(np.int64)
+np.savez_compressed(os.path.join(here, "reference_rollout.npz"), **ro)
+print("wrote", os.path.join(here, "reference_rollout.npz"), [c["in_time"].astype("timedelta64[h]").astype(int).tolist() for c in calls],
+      [c.coords["time"].data.astype("timedelta64[h]").astype(int).tolist() for c in chunks])
