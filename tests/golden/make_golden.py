@@ -399,7 +399,31 @@ for k, (d, v) in api_template.items():
 for path, entry in ns.PARAMS.items():
   for leaf, value in entry.items():
     gnn[f"param:{path}:{leaf}"] = value
+# sanity: the manifest + seed reproduce the parameters bit for bit
+_regen = ns.regenerate(ns.MANIFEST, ns.SEED)
+assert all(np.array_equal(_regen[k][l], v) for k, e in ns.PARAMS.items() for l, v in e.items())
 np.savez_compressed(os.path.join(here, "reference_gnn_forward.npz"), **gnn)
+
+# Same wiring at the CUDA kernels' width (latent 512) for the GPU test: the parameters (40 MB) are
+# not stored, only the seed and the creation manifest they are regenerated from.
+ns.reset(seed=512512)
+cfg512 = ref_gc.ModelConfig(resolution=10.0, mesh_size=2, latent_size=512, gnn_msg_steps=2,
+                            hidden_layers=1, radius_query_fraction_edge_length=0.6)
+model512 = ref_gc.GraphCast(cfg512, task)
+model512._maybe_init(types.SimpleNamespace(lat=glat, lon=glon))
+x512 = np.random.default_rng(1).standard_normal((NLAT * NLON, NB, 9)).astype(np.float32)
+lm512, lg512 = model512._run_grid2mesh_gnn(x512)
+um512 = model512._run_mesh_gnn(lm512)
+out512 = model512._run_mesh2grid_gnn(um512, lg512)
+g512 = {k: v for k, v in gnn.items()
+        if k.split("_")[0] in ("grid", "mesh", "g2m", "m2g") and not k.startswith("grid_features")}
+g512.update(grid_features=x512, output=out512, seed=np.int64(ns.SEED), gnn_msg_steps=np.int64(2),
+            manifest_path=np.array([m[0] for m in ns.MANIFEST]),
+            manifest_kind=np.array([m[1] for m in ns.MANIFEST]),
+            manifest_shape=np.array([[m[2], m[3]] for m in ns.MANIFEST], np.int64),
+            mesh_rms_after_mesh_gnn=np.sqrt(np.mean(um512.astype(np.float64) ** 2)))
+np.savez_compressed(os.path.join(here, "reference_gnn_forward_latent512.npz"), **g512)
+print("wrote", os.path.join(here, "reference_gnn_forward_latent512.npz"), out512.shape, sorted(g512)[:30])
 print("wrote", os.path.join(here, "reference_gnn_forward.npz"), output.shape, len(ns.PARAMS), "param entries")
 
 

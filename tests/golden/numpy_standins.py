@@ -34,7 +34,9 @@ import types
 import numpy as np
 
 PARAMS = collections.OrderedDict()
-_RNG = np.random.default_rng(20240917)
+MANIFEST = []         # (path, leaf, shape) in creation order: enough to regenerate PARAMS from the seed
+SEED = 20240917
+_RNG = np.random.default_rng(SEED)
 _ACTIVE = []          # names of hk.Modules whose __call__ is executing (innermost last)
 DTYPE = np.float32
 
@@ -203,13 +205,46 @@ def _scope(name):
   return f"{_ACTIVE[-1]}/~_networks_builder/{name}"
 
 
-def _truncated_normal(shape, stddev):
-  x = _RNG.standard_normal(shape)
+def _truncated_normal(shape, stddev, rng=None):
+  rng = rng or _RNG
+  x = rng.standard_normal(shape)
   bad = np.abs(x) > 2.0
   while bad.any():
-    x[bad] = _RNG.standard_normal(int(bad.sum()))
+    x[bad] = rng.standard_normal(int(bad.sum()))
     bad = np.abs(x) > 2.0
   return (x * stddev).astype(DTYPE)
+
+
+def _new_linear(fan_in, size, rng=None):
+  rng = rng or _RNG
+  return {"w": _truncated_normal((fan_in, size), 1.0 / np.sqrt(fan_in), rng),
+          "b": (0.1 * rng.standard_normal(size)).astype(DTYPE)}
+
+
+def _new_layer_norm(n, rng=None):
+  rng = rng or _RNG
+  return {"scale": (1.0 + 0.1 * rng.standard_normal(n)).astype(DTYPE),
+          "offset": (0.1 * rng.standard_normal(n)).astype(DTYPE)}
+
+
+def reset(seed):
+  """Fresh parameter store and generator (for a second model in the same process)."""
+  global _RNG, SEED
+  SEED = seed
+  _RNG = np.random.default_rng(seed)
+  PARAMS.clear()
+  del MANIFEST[:]
+
+
+def regenerate(manifest, seed):
+  """The PARAMS a run with this seed created, from its manifest alone (no reference needed):
+  entries are drawn from the same generator in the same order with the same shapes."""
+  rng = np.random.default_rng(int(seed))
+  out = collections.OrderedDict()
+  for path, kind, a, b in manifest:
+    path, kind = str(path), str(kind)
+    out[path] = _new_linear(int(a), int(b), rng) if kind == "linear" else _new_layer_norm(int(a), rng)
+  return out
 
 
 class MLP:
@@ -226,8 +261,8 @@ class MLP:
       key = f"{path}/~/linear_{i}"
       if key not in PARAMS:
         fan_in = x.shape[-1]
-        PARAMS[key] = {"w": _truncated_normal((fan_in, size), 1.0 / np.sqrt(fan_in)),
-                       "b": (0.1 * _RNG.standard_normal(size)).astype(DTYPE)}
+        PARAMS[key] = _new_linear(fan_in, size)
+        MANIFEST.append((key, "linear", fan_in, size))
       p = PARAMS[key]
       if i > 0:
         x = self.activation(x)
@@ -246,8 +281,8 @@ class LayerNorm:
     key = _scope(self.name)
     if key not in PARAMS:
       n = x.shape[-1]
-      PARAMS[key] = {"scale": (1.0 + 0.1 * _RNG.standard_normal(n)).astype(DTYPE),
-                     "offset": (0.1 * _RNG.standard_normal(n)).astype(DTYPE)}
+      PARAMS[key] = _new_layer_norm(n)
+      MANIFEST.append((key, "layer_norm", n, 0))
     p = PARAMS[key]
     mean = x.mean(axis=-1, keepdims=True)
     var = x.var(axis=-1, keepdims=True)              # biased, like hk.LayerNorm
