@@ -1,7 +1,9 @@
 """Oracle: GraphCast encode-process-decode forward on the CPU (torch-CPU tensors).
 
-TEST INFRASTRUCTURE -- see oracle/__init__.py.  PARITY UNPINNED (restatement,
-not executed reference).
+TEST INFRASTRUCTURE -- see oracle/__init__.py.  Pinned against the reference's own wiring,
+executed on numpy stand-ins for jax / jraph / haiku (tests/test_reference_gnn_golden.py,
+tests/test_reference_gnn_latent512.py: 5.5e-7); the third-party primitives listed below are
+restatements of their published definitions (the packages cannot be installed here).
 
 Restates, for explicit index arrays and a Haiku-named parameter dict:
   * hk.nets.MLP + hk.LayerNorm + jraph.concatenated_args as wired by
