@@ -49,6 +49,64 @@ def chunked_prediction(predictor_fn: PredictorFn, rng: Any, inputs, targets_temp
   return xs.concat_time(chunks)
 
 
+def _slice_sample_if_present(inputs: xs.Dataset, forcings, sample_idx):
+  """Member `sample_idx` of inputs / forcings that carry a "sample" dim (reference :310-322)."""
+  if "sample" in inputs.dims:
+    inputs = inputs.isel(sample=sample_idx, drop=True)
+  if forcings is not None and "sample" in forcings.dims:
+    forcings = forcings.isel(sample=sample_idx, drop=True)
+  return inputs, forcings
+
+
+def chunked_prediction_generator_multiple_runs(
+    predictor_fn: PredictorFn, rngs, inputs, targets_template, forcings,
+    num_samples: Optional[int], pmap_devices: Optional[Sequence[Any]] = None,
+    rank: Optional[int] = None, world_size: Optional[int] = None,
+    **chunked_prediction_kwargs) -> Iterator[xs.Dataset]:
+  """Ensemble rollouts: all lead-time chunks of one member, then the next member
+  (reference `chunked_prediction_generator_multiple_runs`, rollout.py:158-306).
+
+  The reference spreads members over `pmap_devices` inside one process.  Here one process
+  drives one GPU, so the equivalent is to give every rank its own block of members: pass
+  `rank` / `world_size` (default: the initialised `torch.distributed` group, else a single
+  rank) and this generator yields only the members of `parallel.members_for_rank`; there is
+  no data-path collective.  Every yielded chunk carries `coords["sample"]` = member index, as
+  in the reference's non-pmap branch.  `pmap_devices` must stay None."""
+  from graphcast_b200 import parallel
+  if pmap_devices is not None:
+    raise ValueError("pmap_devices is not supported: run one process per GPU and pass rank / "
+                     "world_size (or initialise torch.distributed)")
+  inputs = xs.from_xarray(inputs)
+  forcings = xs.from_xarray(forcings) if forcings is not None else None
+  if num_samples is None:
+    if "sample" not in inputs.dims:
+      raise ValueError("The number of samples must be passed when `inputs` don't have a "
+                       "`sample` dim.")
+    num_samples = inputs.sizes["sample"]
+  if "sample" in inputs.dims and num_samples != inputs.sizes["sample"]:
+    raise ValueError("Inconsistent number of samples requested for inputs"
+                     f"{num_samples} != {inputs.sizes['sample']}.")
+  if num_samples != len(rngs):
+    raise ValueError(f"Inconsistent number of rngs passed. {num_samples} != {len(rngs)}.")
+  if forcings is not None and "sample" in forcings.dims and num_samples != forcings.sizes["sample"]:
+    raise ValueError("Inconsistent number of samples requested for forcings"
+                     f"{num_samples} != {forcings.sizes['sample']}.")
+  if rank is None or world_size is None:
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+      rank, world_size = dist.get_rank(), dist.get_world_size()
+    else:
+      rank, world_size = 0, 1
+  for i in parallel.members_for_rank(num_samples, rank, world_size):
+    logging.info("Sample %d/%d", i, num_samples)
+    sample_inputs, sample_forcings = _slice_sample_if_present(inputs, forcings, i)
+    for chunk in chunked_prediction_generator(
+        predictor_fn, rngs[i], inputs=sample_inputs, targets_template=targets_template,
+        forcings=sample_forcings, **chunked_prediction_kwargs):
+      chunk.coords["sample"] = ((), np.asarray(i))
+      yield chunk
+
+
 def chunked_prediction_generator(
     predictor_fn: PredictorFn, rng: Any, inputs, targets_template,
     num_steps_per_chunk: int, forcings=None, verbose: bool = False,

@@ -657,3 +657,46 @@ for i, (chunk, call) in enumerate(zip(chunks, calls)):
 np.savez_compressed(os.path.join(here, "reference_rollout.npz"), **ro)
 print("wrote", os.path.join(here, "reference_rollout.npz"), [c["in_time"].astype("timedelta64[h]").astype(int).tolist() for c in calls],
       [c.coords["time"].data.astype("timedelta64[h]").astype(int).tolist() for c in chunks])
+
+
+# ---- ensemble driver: the reference's chunked_prediction_generator_multiple_runs executed -------
+# Non-pmap branch (one member after the other).  Inputs carry a leading "sample" dim; the stand-in
+# dataset gets `isel(sample=i, drop=True)`, `sizes` including coordinates and item assignment on
+# `coords`.
+_r_isel = RDataset.isel
+
+
+def _r_isel_drop(self, drop=False, **kw):
+  return _r_isel(self, **kw)
+
+
+RDataset.isel = _r_isel_drop
+absl_logging = sys.modules["absl.logging"]
+absl_logging.info = lambda *a, **k: None
+absl_logging.flush = lambda *a, **k: None
+sys.modules["absl"].logging = absl_logging
+ref_rollout.logging = absl_logging
+NS = 3
+ens_inputs_np = {k: ((("sample",) + d) if "time" in d else d,
+                     (np.stack([v * (1.0 + 0.5 * s) for s in range(NS)]) if "time" in d else v))
+                 for k, (d, v) in roll_inputs_np.items()}
+ens_forcings_np = {k: (("sample",) + d, np.stack([v + 0.25 * s for s in range(NS)]))
+                   for k, (d, v) in roll_forcings_np.items()}
+ens_chunks = list(ref_rollout.chunked_prediction_generator_multiple_runs(
+    recording_predictor, rngs=np.arange(NS), inputs=to_rds(ens_inputs_np, in_times),
+    targets_template=to_rds(roll_template_np, tgt_times), forcings=to_rds(ens_forcings_np, tgt_times),
+    num_samples=NS, num_steps_per_chunk=1))
+assert len(ens_chunks) == NS * NSTEPS
+en = {"in_times": ro["in_times"], "target_times": ro["target_times"], "num_samples": np.int64(NS)}
+for tag, spec in (("in", ens_inputs_np), ("forcing", ens_forcings_np), ("template", roll_template_np)):
+  for k, (d, v) in spec.items():
+    en[f"{tag}:{k}"], en[f"{tag}_dims:{k}"] = v, np.array(d)
+for i, chunk in enumerate(ens_chunks):
+  for k in chunk.keys():
+    en[f"chunk{i}:{k}"] = chunk[k].data
+  en[f"chunk{i}_time"] = chunk.coords["time"].data.astype("timedelta64[h]").astype(np.int64)
+  en[f"chunk{i}_sample"] = np.int64(chunk.coords["sample"] if not hasattr(chunk.coords["sample"], "data")
+                                    else chunk.coords["sample"].data)
+np.savez_compressed(os.path.join(here, "reference_rollout_ensemble.npz"), **en)
+print("wrote", os.path.join(here, "reference_rollout_ensemble.npz"),
+      [(int(en[f"chunk{i}_sample"]), en[f"chunk{i}_time"].tolist()) for i in range(len(ens_chunks))])
