@@ -151,6 +151,16 @@ class GraphCast(Predictor):
     self._params = params
     self._engine = None
 
+  def set_precision(self, precision: str) -> None:
+    """Arithmetic mode of the fused layers: "bf16x3" (parity), "bf16", "fp32_simt"."""
+    from graphcast_b200 import _native
+    if precision not in _native.PRECISIONS:
+      raise ValueError(f"unknown precision {precision!r}; expected one of "
+                       f"{sorted(_native.PRECISIONS)}")
+    self._precision = precision
+    if self._engine is not None:
+      self._engine.set_precision(precision)
+
   @property
   def engine(self) -> engine_lib.Engine:
     if self._engine is None:

@@ -87,3 +87,29 @@ def test_extend_targets_template():
   assert ext.sizes["time"] == 40
   assert ext.coords["time"][1][-1] == np.timedelta64(240, "h")
   assert ext.data_vars["temperature"].shape[1] == 40
+
+
+def test_bfloat16_cast_wrapper_semantics():
+  """casting.Bfloat16Cast: a GraphCast is returned itself, switched to the "bf16" mode (so that
+  InputsAndResiduals still fuses); other predictors get a pass-through wrapper; enabled=False
+  changes nothing (reference casting.py:31-65)."""
+  from graphcast_b200 import casting, graphcast
+  cfg = graphcast.ModelConfig(1.0, 5, 512, 16, 1, 0.6)
+  model = graphcast.GraphCast(cfg, graphcast.TASK_13)
+  assert model._precision == "bf16x3"
+  assert casting.Bfloat16Cast(model, enabled=False) is model and model._precision == "bf16x3"
+  wrapped = casting.Bfloat16Cast(model)
+  assert wrapped is model and model._precision == "bf16"
+  try:
+    model.set_precision("fp8")
+    assert False
+  except ValueError:
+    pass
+
+  class Dummy(graphcast.Predictor):
+    def __call__(self, inputs, targets_template, forcings, **kw):
+      return ("called", inputs, targets_template, forcings, kw)
+
+  w = casting.Bfloat16Cast(Dummy())
+  assert isinstance(w, casting.Bfloat16Cast)
+  assert w(1, 2, 3, flag=True) == ("called", 1, 2, 3, {"flag": True})
