@@ -113,3 +113,42 @@ def test_bfloat16_cast_wrapper_semantics():
   w = casting.Bfloat16Cast(Dummy())
   assert isinstance(w, casting.Bfloat16Cast)
   assert w(1, 2, 3, flag=True) == ("called", 1, 2, 3, {"flag": True})
+
+
+def test_autoregressive_predictor_unrolls_like_the_rollout():
+  """autoregressive.Predictor (reference autoregressive.py:127-222): T target steps in one call =
+  the chunked rollout with one step per chunk; validation errors as in the reference."""
+  import pytest
+  from graphcast_b200 import autoregressive, rollout
+  from graphcast_b200 import xarray_shim as xs
+  rng = np.random.default_rng(3)
+  hour = np.timedelta64(6, "h")
+  mk = lambda *s: rng.standard_normal(s).astype(np.float32)
+  inputs = xs.Dataset({"t2m": (("batch", "time", "lat", "lon"), mk(1, 2, 3, 4)),
+                       "toa": (("batch", "time", "lat", "lon"), mk(1, 2, 3, 4)),
+                       "mask": (("lat", "lon"), mk(3, 4))},
+                      coords={"time": np.array([-1, 0]) * hour})
+  tt = (np.arange(3) + 1) * hour
+  template = xs.Dataset({"t2m": (("batch", "time", "lat", "lon"), np.zeros((1, 3, 3, 4), np.float32))},
+                        coords={"time": tt})
+  forcings = xs.Dataset({"toa": (("batch", "time", "lat", "lon"), mk(1, 3, 3, 4))}, coords={"time": tt})
+
+  class OneStep:
+    def __call__(self, inputs, targets_template, forcings, scale=1.0):
+      x = np.asarray(inputs["t2m"].data)
+      f = np.asarray(forcings["toa"].data)
+      y = scale * (0.8 * x[:, 1:] + 0.2 * x[:, :1]) + 0.1 * f + 0.01 * np.asarray(inputs["mask"].data)
+      return xs.Dataset({"t2m": (inputs["t2m"].dims, y)}, coords={"time": targets_template.coords["time"]})
+
+  ar = autoregressive.Predictor(OneStep(), gradient_checkpointing=True)
+  got = ar(inputs, template, forcings, scale=0.5)
+  want = rollout.chunked_prediction(
+      lambda rng, inputs, targets_template, forcings: OneStep()(inputs, targets_template, forcings, scale=0.5),
+      rng=None, inputs=inputs, targets_template=template, forcings=forcings)
+  assert got["t2m"].dims == ("batch", "time", "lat", "lon") and got["t2m"].shape == (1, 3, 3, 4)
+  np.testing.assert_array_equal(np.asarray(got["t2m"].data), np.asarray(want["t2m"].data))
+  np.testing.assert_array_equal(np.asarray(got.coords["time"][1]), tt)
+  with pytest.raises(ValueError, match="Time-dependent input variable"):
+    ar(inputs, template, xs.Dataset(coords={"time": tt}))
+  with pytest.raises(ValueError, match="both targets and forcings"):
+    ar(inputs, template, xs.Dataset({"toa": forcings["toa"], "t2m": template["t2m"]}, coords={"time": tt}))
