@@ -700,3 +700,44 @@ for i, chunk in enumerate(ens_chunks):
 np.savez_compressed(os.path.join(here, "reference_rollout_ensemble.npz"), **en)
 print("wrote", os.path.join(here, "reference_rollout_ensemble.npz"),
       [(int(en[f"chunk{i}_sample"]), en[f"chunk{i}_time"].tolist()) for i in range(len(ens_chunks))])
+
+
+# ---- forcing generation: the reference's progress features and TISR executed ---------------------
+# utils/data_utils.py (get_year_progress, get_day_progress, featurize_progress) and
+# utils/solar_radiation.py (get_tsi, get_toa_incident_solar_radiation with the default ERA5 TSI
+# series) run unmodified; pandas is the real package, jnp is numpy, jax.jit is the identity and
+# jax.scipy.integrate.trapezoid is numpy's.
+jax_mod.jit = lambda f, **kw: f
+jax_mod.scipy = types.SimpleNamespace(integrate=types.SimpleNamespace(trapezoid=np.trapezoid))
+xr_mod.Variable = FakeVariable
+_fda_init = FakeDataArray.__init__
+
+
+def _fda_init_coords(self, data, coords=None, dims=None, name=None):
+  _fda_init(self, data, coords=None, dims=dims, name=name)
+  self.coords = {k: (v if isinstance(v, FakeVariable) else FakeDataArray(np.asarray(v), dims=(k,), name=k))
+                 for k, v in (coords or {}).items()}
+
+
+FakeDataArray.__init__ = _fda_init_coords
+ref_solar = importlib.import_module("weathernext.utils.solar_radiation")
+ref_du = importlib.import_module("weathernext.utils.data_utils")
+stamps = np.array(["2020-02-29T18:00", "1989-11-08T21:00", "2033-07-01T00:00", "2000-01-01T12:00",
+                   "1979-12-31T06:00"], dtype="datetime64[ns]")
+f_lat = np.linspace(-90.0, 90.0, 7)
+f_lon = np.arange(0.0, 360.0, 45.0)
+seconds = stamps.astype("datetime64[s]").astype(np.int64)
+fg = {"timestamps_ns": stamps.astype(np.int64), "lat": f_lat, "lon": f_lon,
+      "year_progress": ref_du.get_year_progress(seconds),
+      "day_progress": ref_du.get_day_progress(seconds, f_lon),
+      "tsi": np.asarray(ref_solar.get_tsi(list(stamps), ref_solar.era5_tsi_data())),
+      "tisr_1h_360": np.asarray(ref_solar.get_toa_incident_solar_radiation(list(stamps), f_lat, f_lon)),
+      "tisr_6h_24_reference_tsi": np.asarray(ref_solar.get_toa_incident_solar_radiation(
+          list(stamps[:2]), f_lat, f_lon, tsi_data=ref_solar.reference_tsi_data(),
+          integration_period="6h", num_integration_bins=24))}
+feat = ref_du.featurize_progress("day_progress", ("time", "lon"), fg["day_progress"])
+for k, v in feat.items():
+  fg["feat:" + k], fg["feat_dims:" + k] = v.data, np.array(v.dims)
+np.savez_compressed(os.path.join(here, "reference_forcings.npz"), **fg)
+print("wrote", os.path.join(here, "reference_forcings.npz"), fg["tisr_1h_360"].shape, fg["tisr_1h_360"].dtype,
+      float(fg["tisr_1h_360"].max()), fg["tsi"])
