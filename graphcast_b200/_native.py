@@ -102,6 +102,8 @@ EXPORTS = {
                                           _fp, _fp, _fp]),
     "gcb_forward": (C.c_int, [C.POINTER(Model), _fp, _fp, _fp, C.POINTER(C.c_int32)]),
     "gcb_set_cluster_size": (C.c_int, [C.c_int32]),
+    "gcb_toa_incident_solar_radiation": (C.c_int, [_fp, C.c_int32, C.c_int32, _fp, _fp, _fp, _fp,
+                                         C.c_int32, C.c_int32, _fp, _fp]),
     "gcb_set_graph_replay": (C.c_int, [C.c_int32]),
     "gcb_debug_trace": (C.c_int, [_fp]),
     "gcb_debug_flags": (C.c_int, [C.c_int]),

@@ -524,6 +524,26 @@ int gcb_unpack_grid_outputs(const float* y, int32_t ld_y, int32_t n_out, int64_t
   return GCB_OK;
 }
 
+int gcb_toa_incident_solar_radiation(const float* table, int32_t n_times, int32_t bins,
+                                     const float* sin_lat, const float* cos_lat,
+                                     const float* cos_lon, const float* sin_lon, int32_t n_lat,
+                                     int32_t n_lon, float* out, void* stream) {
+  GCB_CHECK_ARG(table && sin_lat && cos_lat && cos_lon && sin_lon && out, "null pointer");
+  GCB_CHECK_ARG(bins >= 1 && bins <= 2048, "bins must be in [1, 2048]");
+  GCB_CHECK_ARG(n_times >= 0 && n_times <= 65535 && n_lat >= 0 && n_lat <= 65535 && n_lon >= 0,
+                "grid too large");
+  if (n_times == 0 || n_lat == 0 || n_lon == 0) return GCB_OK;
+  dim3 grid(static_cast<unsigned>((n_lon + 255) / 256), static_cast<unsigned>(n_lat),
+            static_cast<unsigned>(n_times));
+  ProfScope prof(static_cast<cudaStream_t>(stream), GCB_KIND_PACK, 0.0,
+                 4.0 * n_times * static_cast<double>(n_lat) * n_lon);
+  gcb::tisr_kernel<<<grid, 256, static_cast<size_t>(bins) * 5 * sizeof(float),
+                     static_cast<cudaStream_t>(stream)>>>(
+      table, bins, sin_lat, cos_lat, cos_lon, sin_lon, n_lat, n_lon, out);
+  GCB_CUDA(cudaGetLastError());
+  return GCB_OK;
+}
+
 int gcb_rows_to_image(const float* src, int32_t ld, int32_t fan, int64_t rows, int32_t k,
                       void* img, void* stream) {
   GCB_CHECK_ARG(src && img && aligned16(src) && aligned16(img), "null/unaligned pointer");

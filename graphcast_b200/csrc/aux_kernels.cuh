@@ -220,6 +220,36 @@ pack_grid_image_kernel(const float* __restrict__ planes, int n_ch, long long n_n
   }
 }
 
+// TOA incident solar radiation (the reference's solar_radiation.get_toa_incident_solar_radiation,
+// :443-521): out[t, h, w] = sum_b f[t,b] * max(cos_lat[h] * cd[t,b] * cos(H0[t,b] + lon[w]) +
+// sin_lat[h] * sd[t,b], 0), the trapezoidal time integral of the instantaneous flux.  The per-bin
+// orbital quantities are scalars computed on the host in float64 (`table`: [T, B, 5] =
+// cos / sin of the declination, cos / sin of the hour angle at longitude 0, and
+// weight * TSI / d^2 * dx); cos(H0 + lon) is expanded with the angle-sum identity, so the bin loop
+// has no transcendental.  One thread per grid point, the bin table of the block's timestamp in
+// shared memory; reads 3 small vectors, writes the field once (HBM-bound at 0.25 degree).
+__global__ void __launch_bounds__(256)
+tisr_kernel(const float* __restrict__ table, int bins, const float* __restrict__ sin_lat,
+            const float* __restrict__ cos_lat, const float* __restrict__ cos_lon,
+            const float* __restrict__ sin_lon, int n_lat, int n_lon, float* __restrict__ out) {
+  extern __shared__ float s_tab[];                  // [bins][5]
+  const int t = blockIdx.z, h = blockIdx.y;
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* tab = table + static_cast<size_t>(t) * bins * 5;
+  for (int i = threadIdx.x; i < bins * 5; i += blockDim.x) s_tab[i] = tab[i];
+  __syncthreads();
+  if (w >= n_lon) return;
+  const float sl = sin_lat[h], cl = cos_lat[h], cw = cos_lon[w], sw = sin_lon[w];
+  float acc = 0.f;
+  for (int b = 0; b < bins; ++b) {
+    const float* p = s_tab + 5 * b;
+    const float cos_h = p[2] * cw - p[3] * sw;      // cos(H0 + lon)
+    const float sin_alt = fmaf(cl * p[0], cos_h, sl * p[1]);
+    acc = fmaf(p[4], fmaxf(sin_alt, 0.f), acc);
+  }
+  out[(static_cast<size_t>(t) * n_lat + h) * n_lon + w] = acc;
+}
+
 // y [n_nodes, ld_y] -> planes_out [n_out, n_nodes] with per-channel affine and an
 // optional additive plane (the last input frame for residual targets).
 __global__ void __launch_bounds__(256)

@@ -207,3 +207,50 @@ def add_tisr_var(data: xs.Dataset) -> None:
   flat = get_toa_incident_solar_radiation(dt.reshape(-1), lat, lon)
   tisr = flat.reshape(dt.shape + flat.shape[1:]).astype(np.float32)
   data[TISR] = (tuple(dt_dims) + ("lat", "lon"), tisr)
+
+
+# ---- device version -------------------------------------------------------------------------------
+def _integration_table(timestamps: np.ndarray, tsi_data, integration_period, num_integration_bins
+                       ) -> np.ndarray:
+  """[T, bins + 1, 5] float32 for `gcb_toa_incident_solar_radiation`: per integration bin the
+  cos / sin of the solar declination, the cos / sin of the hour angle at longitude 0 and
+  weight * TSI / d^2 * dx (all scalars per timestamp and bin, computed in float64)."""
+  ts = np.asarray(timestamps, dtype="datetime64[ns]").reshape(-1)
+  tsi = get_tsi(ts, tsi_data if tsi_data is not None else era5_tsi_data())
+  period_days = np.timedelta64(integration_period).astype("timedelta64[ns]").astype(np.int64) / (SEC_PER_DAY * 1e9)
+  offsets = np.linspace(-period_days, 0.0, num_integration_bins + 1)
+  dx = period_days * SEC_PER_DAY / num_integration_bins
+  weights = np.ones(num_integration_bins + 1)
+  weights[[0, -1]] = 0.5
+  days = _j2000_days(ts)[:, None] + offsets[None, :]                     # [T, bins + 1]
+  phase, sin_decl, cos_decl, eot, dist = _orbital_parameters(days)
+  h0 = 2.0 * np.pi * (phase + eot / SEC_PER_DAY)
+  factor = weights[None, :] * tsi[:, None] * (1.0 / dist) ** 2 * dx
+  return np.stack([cos_decl, sin_decl, np.cos(h0), np.sin(h0), factor], axis=-1).astype(np.float32)
+
+
+def get_toa_incident_solar_radiation_device(
+    timestamps: Sequence, latitude: np.ndarray, longitude: np.ndarray, device=None,
+    tsi_data: Optional[Tuple[np.ndarray, np.ndarray]] = None,
+    integration_period=np.timedelta64(1, "h"), num_integration_bins: int = 360):
+  """Same quantity as `get_toa_incident_solar_radiation`, computed on the GPU
+  (`gcb_toa_incident_solar_radiation`): returns a float32 torch tensor [time, lat, lon] on
+  `device`.  The orbital scalars per (timestamp, bin) are prepared here in float64; the kernel
+  does the [lat, lon] field work (0.25 degree: one pass, 4 MB written per timestamp)."""
+  import torch
+  from graphcast_b200 import _native
+  lib = _native.lib()
+  dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+  table = _integration_table(timestamps, tsi_data, integration_period, num_integration_bins)
+  lat = np.radians(np.asarray(latitude, dtype=np.float64))
+  lon = np.radians(np.asarray(longitude, dtype=np.float64))
+  up = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+  t_tab, s_lat, c_lat, c_lon, s_lon = (up(table), up(np.sin(lat)), up(np.cos(lat)),
+                                       up(np.cos(lon)), up(np.sin(lon)))
+  out = torch.empty((table.shape[0], lat.shape[0], lon.shape[0]), dtype=torch.float32, device=dev)
+  with torch.cuda.device(dev):
+    _native.check(lib.gcb_toa_incident_solar_radiation(
+        t_tab.data_ptr(), table.shape[0], table.shape[1], s_lat.data_ptr(), c_lat.data_ptr(),
+        c_lon.data_ptr(), s_lon.data_ptr(), lat.shape[0], lon.shape[0], out.data_ptr(),
+        torch.cuda.current_stream(dev).cuda_stream), "gcb_toa_incident_solar_radiation")
+  return out

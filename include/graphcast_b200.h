@@ -192,6 +192,19 @@ int gcb_unpack_grid_outputs(const float* y, int32_t ld_y, int32_t n_out, int64_t
                             const float* add_planes, const int32_t* add_plane_index,
                             float* planes_out, void* stream);
 
+/* Top-of-atmosphere incident solar radiation on a lat / lon grid, integrated over a period ending
+ * at each timestamp (replaces solar_radiation.get_toa_incident_solar_radiation,
+ * weathernext/utils/solar_radiation.py:443-521; the forcing GraphCast needs at every target time).
+ *   table   [n_times, bins, 5] (device): per integration bin cos / sin of the solar declination,
+ *           cos / sin of the hour angle at longitude 0, and weight * TSI / d_au^2 * dx - host-side
+ *           scalars, see graphcast_b200/forcings.py
+ *   sin_lat, cos_lat [n_lat]; cos_lon, sin_lon [n_lon] (device)
+ *   out     [n_times, n_lat, n_lon] float32, J/m^2. */
+int gcb_toa_incident_solar_radiation(const float* table, int32_t n_times, int32_t bins,
+                                     const float* sin_lat, const float* cos_lat,
+                                     const float* cos_lon, const float* sin_lon, int32_t n_lat,
+                                     int32_t n_lon, float* out, void* stream);
+
 /* ---- whole-step orchestration -------------------------------------------------- */
 
 /* One two-layer MLP (+ optional LayerNorm) of the model. */

@@ -71,3 +71,38 @@ def test_add_derived_vars_and_tisr_on_a_dataset(ref):
   np.testing.assert_allclose(np.asarray(tisr.data)[0], ref["tisr_1h_360"][:3], rtol=1e-6)
   with pytest.raises(ValueError, match="datetime"):
     forcings.add_derived_vars(xs.Dataset(coords={"lon": ref["lon"]}))
+
+
+def test_device_table_reproduces_the_host_integral(ref):
+  """The float64 -> float32 bin table of the CUDA version, evaluated with the kernel's own formula
+  in numpy (float32 accumulation), gives the host / reference integral."""
+  table = forcings._integration_table(_stamps(ref), None, np.timedelta64(1, "h"), 360)
+  assert table.shape == (5, 361, 5) and table.dtype == np.float32
+  lat, lon = np.radians(ref["lat"]), np.radians(ref["lon"])
+  sl, cl = np.sin(lat).astype(np.float32)[:, None], np.cos(lat).astype(np.float32)[:, None]
+  cw, sw = np.cos(lon).astype(np.float32)[None, :], np.sin(lon).astype(np.float32)[None, :]
+  out = np.zeros((5, 7, 8), np.float32)
+  for t in range(5):
+    for b in range(361):
+      cd, sd, ch, sh, f = table[t, b]
+      sin_alt = (cl * cd) * (ch * cw - sh * sw) + sl * sd
+      out[t] += f * np.maximum(sin_alt, np.float32(0))
+  want = ref["tisr_1h_360"]
+  assert np.abs(out - want).max() <= 2e-6 * want.max()
+
+
+@pytest.mark.gpu
+def test_tisr_cuda_kernel_matches_executed_reference(ref):
+  import torch
+  got = forcings.get_toa_incident_solar_radiation_device(_stamps(ref), ref["lat"], ref["lon"])
+  torch.cuda.synchronize()
+  want = ref["tisr_1h_360"]
+  err = np.abs(got.cpu().numpy() - want).max() / want.max()
+  print(f"TISR CUDA kernel vs executed reference: max-abs error / max {err:.2e}")
+  assert got.shape == want.shape and err <= 1e-5
+  # a larger, ragged grid against the host mirror (non-multiple-of-256 longitude count)
+  lat, lon = np.linspace(-90, 90, 91), np.arange(0, 360, 0.7)
+  stamps = _stamps(ref)[:2]
+  host = forcings.get_toa_incident_solar_radiation(stamps, lat, lon)
+  dev = forcings.get_toa_incident_solar_radiation_device(stamps, lat, lon).cpu().numpy()
+  assert np.abs(dev - host).max() <= 1e-5 * host.max()
