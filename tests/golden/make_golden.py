@@ -741,3 +741,88 @@ for k, v in feat.items():
 np.savez_compressed(os.path.join(here, "reference_forcings.npz"), **fg)
 print("wrote", os.path.join(here, "reference_forcings.npz"), fg["tisr_1h_360"].shape, fg["tisr_1h_360"].dtype,
       float(fg["tisr_1h_360"].max()), fg["tsi"])
+
+
+# ---- example batch -> (inputs, targets, forcings): the reference's data_utils executed -----------
+# `extract_inputs_targets_forcings` / `extract_input_target_times` (data_utils.py:214-333) run
+# unmodified with real pandas Timedeltas; the stand-in dataset gets label selection (`sel` on
+# level / time, inclusive slices), `drop_vars` and integer indexing of a coordinate.
+import pandas as pd  # noqa: E402
+
+
+def _labels(values):
+  return np.asarray([np.timedelta64(pd.Timedelta(v).value, "ns") if isinstance(v, (pd.Timedelta, str)) else v
+                     for v in values])
+
+
+def _r_sel(self, indexers=None, **kw):
+  indexers = dict(indexers or {}, **kw)
+  out = self
+  for dim, sel in indexers.items():
+    coord = out.coords[dim].data
+    if isinstance(sel, slice):
+      lo, hi = _labels([sel.start])[0], _labels([sel.stop])[0]
+      idx = np.flatnonzero((coord >= lo) & (coord <= hi))
+    else:
+      idx = np.asarray([int(np.flatnonzero(coord == l)[0]) for l in _labels(list(sel))])
+    data = {k: (FakeDataArray(np.take(v.data, idx, axis=v.dims.index(dim)), dims=v.dims, name=k)
+                if dim in v.dims else v) for k, v in out.items()}
+    coords = {k: (FakeDataArray(np.take(c.data, idx, axis=c.dims.index(dim)), dims=c.dims, name=k)
+                  if dim in c.dims else c) for k, c in out.coords.items()}
+    out = RDataset(data, coords)
+  return out
+
+
+RDataset.sel = _r_sel
+RDataset.drop_vars = lambda self, name: RDataset(dict(self), {k: c for k, c in self.coords.items() if k != name})
+FakeVariable.__getitem__ = lambda self, i: FakeDataArray(self.data[i], dims=self.dims[1:], name=getattr(self, "name", None))
+_prev_binary = _binary
+
+
+def _binary_td(a, b, op):
+  if isinstance(b, pd.Timedelta):
+    b = np.timedelta64(b.value, "ns")
+  return _prev_binary(a, b, op)
+
+
+FakeVariable.__sub__ = lambda a, b: _binary_td(a, b, np.subtract)
+FakeVariable.__add__ = lambda a, b: _binary_td(a, b, np.add)
+rngd = np.random.default_rng(21)
+mkd = lambda *s: rngd.standard_normal(s).astype(np.float32)
+DB, DT, DL, DLAT, DLON = 2, 5, 4, 3, 4
+batch_np = {
+    "2m_temperature": (("batch", "time", "lat", "lon"), mkd(DB, DT, DLAT, DLON)),
+    "geopotential": (("batch", "time", "level", "lat", "lon"), mkd(DB, DT, DL, DLAT, DLON)),
+    "toa_incident_solar_radiation": (("batch", "time", "lat", "lon"), mkd(DB, DT, DLAT, DLON)),
+    "land_sea_mask": (("lat", "lon"), mkd(DLAT, DLON)),
+}
+d_time = (np.arange(DT) * np.timedelta64(6, "h")).astype("timedelta64[ns]")
+d_level = np.array([50, 500, 850, 1000])
+d_datetime = (np.datetime64("2021-03-04T00:00", "ns") + d_time)[None].repeat(DB, 0)
+example = RDataset(
+    {k: FakeDataArray(v, dims=d, name=k) for k, (d, v) in batch_np.items()},
+    {"time": FakeDataArray(d_time, dims=("time",), name="time"),
+     "level": FakeDataArray(d_level, dims=("level",), name="level"),
+     "lat": FakeDataArray(np.linspace(-45, 45, DLAT), dims=("lat",), name="lat"),
+     "lon": FakeDataArray(np.arange(DLON) * 90.0, dims=("lon",), name="lon"),
+     "datetime": FakeDataArray(d_datetime, dims=("batch", "time"), name="datetime")})
+du = {"time_ns": d_time.astype(np.int64), "level": d_level, "datetime_ns": d_datetime.astype(np.int64)}
+for k, (d, v) in batch_np.items():
+  du[f"in:{k}"], du[f"in_dims:{k}"] = v, np.array(d)
+task_kw = dict(input_variables=("2m_temperature", "geopotential", "toa_incident_solar_radiation", "land_sea_mask"),
+               target_variables=("2m_temperature", "geopotential"),
+               forcing_variables=("toa_incident_solar_radiation",), pressure_levels=(500, 1000),
+               input_duration="12h")
+for tag, lead in (("slice", slice("6h", "18h")), ("list", ["12h"])):
+  parts = ref_du.extract_inputs_targets_forcings(example, target_lead_times=lead, **task_kw)
+  for part_name, part in zip(("inputs", "targets", "forcings"), parts):
+    du[f"{tag}:{part_name}:time_ns"] = part.coords["time"].data.astype("timedelta64[ns]").astype(np.int64)
+    du[f"{tag}:{part_name}:names"] = np.array(sorted(part.keys()))
+    assert "datetime" not in part.coords
+    for k in part.keys():
+      du[f"{tag}:{part_name}:{k}"] = part[k].data
+      du[f"{tag}:{part_name}_dims:{k}"] = np.array(part[k].dims)
+np.savez_compressed(os.path.join(here, "reference_data_utils.npz"), **du)
+print("wrote", os.path.join(here, "reference_data_utils.npz"),
+      {t: (du[f"{t}:inputs:time_ns"] // 3600e9).tolist() for t in ("slice", "list")},
+      {t: (du[f"{t}:targets:time_ns"] // 3600e9).tolist() for t in ("slice", "list")})
