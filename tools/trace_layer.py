@@ -1,4 +1,13 @@
-"""Timeline of CTA 0 for one fused-layer launch (debug aid)."""
+"""Timeline of CTA 0 for one fused-layer launch (debug aid).
+
+  python tools/trace_layer.py            # six layer shapes, 1184 tiles
+  python tools/trace_layer.py big        # two image-fed shapes at 3.0M rows (HBM resident)
+  python tools/trace_layer.py flags      # attribution sweep over gcb_debug_flags (2, 4, 16)
+  python tools/trace_layer.py cluster    # cluster 1 vs 2, with / without global stores
+
+Columns: cycles (clock64) of the MMA warp / epilogue of the first units, plus the cycles the MMA
+warp spent waiting on `full` barriers (mma_starved) and the TMA warp on `empty` barriers
+(tma_blocked) per unit."""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -57,7 +66,7 @@ def run(rows, k, n, ln, act, csize, out_y=False, residual=False, idx=False, pre=
     r = t[i]
     print(f"  tile {i}: acc_free@{r[0]-base:7d} ops_ready+{r[1]-r[0]:6d} mma_issue+{r[2]-r[1]:6d} | "
           f"epi_start(after commit)+{r[3]-r[2]:6d} ln_stats+{r[4]-r[3]:6d} store+{r[5]-r[4]:6d} | "
-          f"next_acc_free+{t[i+1,0]-r[5]:6d}  tile_total={t[i+1,0]-r[0]} | mma_starved={r[6]} tma_blocked={r[7]} tma_head={r[8]} expect={r[9]} acopy={r[10]} bcopy={r[11]}")
+          f"next_acc_free+{t[i+1,0]-r[5]:6d}  tile_total={t[i+1,0]-r[0]} | mma_starved={r[6]} tma_blocked={r[7]}")
 
 import sys
 big = len(sys.argv) > 1 and sys.argv[1] in ("big", "flags", "cluster")
@@ -72,9 +81,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "cluster":
   sys.exit(0)
 rows = 148 * 128 * (160 if big else 8)
 if len(sys.argv) > 1 and sys.argv[1] == "flags":
-  # attribution sweep: 1 A from tile 0 (L2 hits) | 2 no stores | 4 no A multicast |
-  # 8 B block 0 only | 16 L2 prefetch | 32 no A load
-  for fl in (0, 1, 2, 3, 4, 8, 32, 1 | 2 | 8, 32 | 2 | 8):
+  # attribution sweep: 2 no global stores | 4 N-split pair without A multicast | 16 L2 prefetch
+  for fl in (0, 2, 4, 16, 2 | 4):
     print(f"==== debug flags {fl}")
     lib.gcb_debug_flags(fl)
     run(rows, 512, 512, False, True, 2, img_in=True, img_out=True)
