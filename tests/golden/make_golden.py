@@ -826,3 +826,13 @@ np.savez_compressed(os.path.join(here, "reference_data_utils.npz"), **du)
 print("wrote", os.path.join(here, "reference_data_utils.npz"),
       {t: (du[f"{t}:inputs:time_ns"] // 3600e9).tolist() for t in ("slice", "list")},
       {t: (du[f"{t}:targets:time_ns"] // 3600e9).tolist() for t in ("slice", "list")})
+
+
+# ---- variable tables (weathernext/utils/variables.py is plain data and imports fine) -------------
+from weathernext.utils import variables as ref_vars  # noqa: E402
+
+vt = {name: np.array(getattr(ref_vars, name)) for name in dir(ref_vars)
+      if name.isupper() and isinstance(getattr(ref_vars, name), tuple)}
+vt["PRESSURE_LEVELS_keys"] = np.array(sorted(ref_vars.PRESSURE_LEVELS))
+np.savez_compressed(os.path.join(here, "reference_variables.npz"), **vt)
+print("wrote", os.path.join(here, "reference_variables.npz"), sorted(vt))
