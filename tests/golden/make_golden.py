@@ -836,3 +836,14 @@ vt = {name: np.array(getattr(ref_vars, name)) for name in dir(ref_vars)
 vt["PRESSURE_LEVELS_keys"] = np.array(sorted(ref_vars.PRESSURE_LEVELS))
 np.savez_compressed(os.path.join(here, "reference_variables.npz"), **vt)
 print("wrote", os.path.join(here, "reference_variables.npz"), sorted(vt))
+
+
+# ---- task definitions (weathernext1_graph/graphcast.py:86-112), via the stand-in import ----------
+tk = {}
+for tname in ("TASK", "TASK_13", "TASK_13_PRECIP_OUT"):
+  t = getattr(ref_gc, tname)
+  for field in ("input_variables", "target_variables", "forcing_variables", "pressure_levels"):
+    tk[f"{tname}:{field}"] = np.array(getattr(t, field))
+  tk[f"{tname}:input_duration"] = np.array(t.input_duration)
+np.savez_compressed(os.path.join(here, "reference_tasks.npz"), **tk)
+print("wrote", os.path.join(here, "reference_tasks.npz"), {k: len(v) for k, v in tk.items() if v.ndim})
