@@ -22,7 +22,7 @@ runs in libgraphcast_b200.so.  HBM layout (fp32 unless noted):
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Mapping, Optional
+from typing import Mapping, Optional
 
 import numpy as np
 import torch

@@ -18,7 +18,7 @@ with the trapezoidal rule on `num_integration_bins` bins.  The integration loop 
 
 from __future__ import annotations
 
-from typing import Dict, Mapping, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 
