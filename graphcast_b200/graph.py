@@ -151,7 +151,7 @@ def cached_static_graph(*, grid_lat: np.ndarray, grid_lon: np.ndarray,
   h.update(np.ascontiguousarray(grid_lat, dtype=np.float32).tobytes())
   h.update(np.ascontiguousarray(grid_lon, dtype=np.float32).tobytes())
   h.update(repr((mesh_size, float(radius_query_fraction_edge_length),
-                 mesh2grid_edge_normalization_factor, "v2")).encode())
+                 mesh2grid_edge_normalization_factor, "v3")).encode())
   path = os.path.join(cache_dir, f"connectivity_{h.hexdigest()[:16]}.npz")
   build = lambda conn: build_static_graph(
       grid_lat=grid_lat, grid_lon=grid_lon, mesh_size=mesh_size,

@@ -100,7 +100,12 @@ def _split_faces_once(mesh: TriangularMesh) -> TriangularMesh:
   pa = a[first_pos[order]]
   pb = b[first_pos[order]]
   mid = (v[pa] + v[pb]) / np.float32(2.0)
-  norm = np.sqrt(np.sum(mid * mid, axis=-1, dtype=np.float32), dtype=np.float32)
+  # The reference divides every child by `np.linalg.norm(child)` (:344), i.e. sqrt(BLAS sdot)
+  # of a 3-vector; a vectorised sum of squares rounds differently in the last bit for some
+  # vertices, which is enough to flip radius-query ties at 0.25 degree.  Same call, per vertex.
+  norm = np.empty([mid.shape[0]], np.float32)
+  for i in range(mid.shape[0]):
+    norm[i] = np.linalg.norm(mid[i])
   mid = (mid / norm[:, None]).astype(np.float32)
   vertices = np.concatenate([v, mid], axis=0)
 
@@ -150,7 +155,10 @@ def faces_to_edges(faces: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
   return senders.copy(), receivers.copy()
 
 
-def max_edge_length(mesh: TriangularMesh) -> float:
-  """Longest edge of the mesh in R^3 (reference graphcast.py:733-737)."""
+def max_edge_length(mesh: TriangularMesh) -> np.float32:
+  """Longest edge of the mesh in R^3 (reference graphcast.py:733-737).  Returned as the
+  numpy float32 scalar the reference's `_get_max_edge_distance` yields, so that
+  `max_edge * radius_query_fraction_edge_length` (graphcast.py:266-267) goes through the
+  same numpy promotion (float32 under NEP 50) and the query radius is bit-identical."""
   s, r = faces_to_edges(mesh.faces)
-  return float(np.linalg.norm(mesh.vertices[s] - mesh.vertices[r], axis=-1).max())
+  return np.linalg.norm(mesh.vertices[s] - mesh.vertices[r], axis=-1).max()

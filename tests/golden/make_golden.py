@@ -28,6 +28,7 @@ for splits in range(0, 7):
     out[f"vertices_{splits}"] = verts
     out[f"faces_{splits}"] = faces
   out[f"faces_sha_{splits}"] = np.frombuffer(hashlib.sha256(faces.tobytes()).digest(), np.uint8)
+  out[f"vertices_sha_{splits}"] = np.frombuffer(hashlib.sha256(verts.tobytes()).digest(), np.uint8)
   out[f"vertex_sum_{splits}"] = verts.astype(np.float64).sum(0)
   out[f"vertex_abs_sum_{splits}"] = np.abs(verts.astype(np.float64)).sum(0)
   merged = ref.merge_meshes(meshes)
@@ -176,6 +177,29 @@ for tag, norm in (("", None), ("_norm2", 2.0)):
       edge_normalization_factor=norm, **kw)
   geo["m2g_edge_feats" + tag] = ef3
 np.savez_compressed(os.path.join(here, "reference_geometry.npz"), **geo)
+
+# Grid->mesh connectivity at the BASELINE resolutions, by the reference's own
+# `radius_query_indices` on the reference's own mesh (utils/legacy/grid_mesh_connectivity.py:40-86,
+# grid exactly as GraphCast._init_grid_properties builds it, graphcast.py:396-406): edge count and
+# sha256 of the int64 index arrays.  The radius query is tie-sensitive (1-ulp vertex differences
+# flip edges at 0.25 degree), so index parity is pinned at the sizes the benchmark runs.
+conn = {}
+for tag, res, splits in (("1deg_mesh5", 1.0, 5), ("0p25deg_mesh6", 0.25, 6)):
+  clat = np.linspace(-90, 90, int(round(180 / res)) + 1).astype(np.float32)
+  clon = (np.arange(int(round(360 / res))) * res).astype(np.float32)
+  cmesh = ref.get_hierarchy_of_triangular_meshes_for_sphere(splits)[-1]
+  ces, cer = ref.faces_to_edges(cmesh.faces)
+  cmax = np.linalg.norm(cmesh.vertices[ces] - cmesh.vertices[cer], axis=-1).max()
+  gi, mi = ref_gm.radius_query_indices(grid_latitude=clat, grid_longitude=clon, mesh=cmesh,
+                                       radius=0.6 * cmax)
+  gi, mi = np.ascontiguousarray(gi, np.int64), np.ascontiguousarray(mi, np.int64)
+  conn[f"num_edges_{tag}"] = np.int64(gi.shape[0])
+  conn[f"grid_sha_{tag}"] = np.frombuffer(hashlib.sha256(gi.tobytes()).digest(), np.uint8)
+  conn[f"mesh_sha_{tag}"] = np.frombuffer(hashlib.sha256(mi.tobytes()).digest(), np.uint8)
+  conn[f"radius_{tag}"] = np.float64(0.6 * cmax)
+np.savez_compressed(os.path.join(here, "reference_connectivity.npz"), **conn)
+print("wrote reference_connectivity.npz", {k: (int(v) if v.ndim == 0 and v.dtype.kind == "i" else v.shape)
+                                          for k, v in conn.items()})
 print("wrote", os.path.join(here, "reference_geometry.npz"),
       {k: (v.shape, str(v.dtype)) for k, v in geo.items() if hasattr(v, "shape")})
 
