@@ -492,11 +492,14 @@ int gcb_pack_grid_image(const float* planes, int32_t n_ch, int64_t n_nodes, cons
   if (n_nodes == 0) return GCB_OK;
   const size_t smem = 32 * static_cast<size_t>(k + 4) * sizeof(float);
   GCB_CHECK_ARG(smem <= 96 * 1024, "k too large");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};     // per device: the opt-in is a per-context attribute
+  int dev = 0;
+  GCB_CUDA(cudaGetDevice(&dev));
+  GCB_CHECK_ARG(dev >= 0 && dev < 64, "device index out of range");
+  if (!attr_set[dev]) {
     GCB_CUDA(cudaFuncSetAttribute(gcb::pack_grid_image_kernel,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const long long padded = (n_nodes + 127) / 128 * 128;
   ProfScope prof(static_cast<cudaStream_t>(stream), GCB_KIND_PACK, 0.0,
@@ -550,11 +553,14 @@ int gcb_rows_to_image(const float* src, int32_t ld, int32_t fan, int64_t rows, i
   GCB_CHECK_ARG(k > 0 && k % 16 == 0 && ld % 4 == 0 && ld >= k && fan >= 1, "bad k / ld / fan");
   if (rows == 0) return GCB_OK;
   const size_t smem = 32 * static_cast<size_t>(k + 4) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};     // per device: the opt-in is a per-context attribute
+  int dev = 0;
+  GCB_CUDA(cudaGetDevice(&dev));
+  GCB_CHECK_ARG(dev >= 0 && dev < 64, "device index out of range");
+  if (!attr_set[dev]) {
     GCB_CUDA(cudaFuncSetAttribute(gcb::rows_to_image_kernel,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   GCB_CHECK_ARG(smem <= 96 * 1024, "k too large");
   const long long padded = (rows + 127) / 128 * 128;      // zero-fill the tail of the last tile

@@ -257,9 +257,10 @@ class Engine:
     self.grid_agg_img = self._image(m.num_grid)
     self.grid_out = f(m.num_grid, 256)
     # static mesh-node encoder input as an image, built once
-    _native.check(self._lib.gcb_rows_to_image(self.mesh_in.data_ptr(), self.c_in_pad, 1, m.num_mesh,
-                                              self.c_in_pad, self.mesh_in_img.data_ptr(),
-                                              self._stream()), "gcb_rows_to_image")
+    with self._on_device():
+      _native.check(self._lib.gcb_rows_to_image(self.mesh_in.data_ptr(), self.c_in_pad, 1, m.num_mesh,
+                                                self.c_in_pad, self.mesh_in_img.data_ptr(),
+                                                self._stream()), "gcb_rows_to_image")
     for name in ("hidden", "edge_a_img", "edge_b", "mesh_in_img", "grid_lat",
                  "grid_lat_img", "mesh_lat", "mesh_lat_img", "mesh_agg", "mesh_agg_img",
                  "mesh_edge", "mesh_edge_img", "mesh_msg", "grid_agg_img"):
@@ -280,9 +281,13 @@ class Engine:
     return sum(t.numel() * t.element_size() for t in ts)
 
   # -- execution ---------------------------------------------------------------------
-  @staticmethod
-  def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+  def _stream(self) -> int:
+    """Raw handle of the current stream of THIS engine's device (not of the current device)."""
+    return torch.cuda.current_stream(self.device).cuda_stream
+
+  def _on_device(self):
+    """The C ABI launches on the calling thread's current CUDA device; make that ours."""
+    return torch.cuda.device(self.device)
 
   def set_precision(self, precision: str) -> None:
     self._model.precision = _native.PRECISIONS[precision]
@@ -298,10 +303,11 @@ class Engine:
       raise ValueError(f"planes must be a contiguous fp32 [{self.c_in}, {self.num_grid}] "
                        f"tensor on {self.device}")
     out = self.grid_in_img if out is None else out
-    _native.check(self._lib.gcb_pack_grid_image(
-        planes.data_ptr(), self.c_in, self.num_grid, self._ptr(mean), self._ptr(scale),
-        self.grid_static.data_ptr(), 3, self.c_in_pad, out.data_ptr(), self._stream()),
-        "gcb_pack_grid_image")
+    with self._on_device():
+      _native.check(self._lib.gcb_pack_grid_image(
+          planes.data_ptr(), self.c_in, self.num_grid, self._ptr(mean), self._ptr(scale),
+          self.grid_static.data_ptr(), 3, self.c_in_pad, out.data_ptr(), self._stream()),
+          "gcb_pack_grid_image")
     return out
 
   def step(self, grid_in: Optional[torch.Tensor] = None,
@@ -319,9 +325,10 @@ class Engine:
         self._step_stream = torch.cuda.Stream(self.device)
       self._step_stream.wait_stream(cur)
     st = self._step_stream if side else cur
-    _native.check(self._lib.gcb_forward(C.byref(self._model), grid_in.data_ptr(),
-                                        grid_out.data_ptr(), st.cuda_stream, C.byref(n)),
-                  "gcb_forward")
+    with self._on_device():
+      _native.check(self._lib.gcb_forward(C.byref(self._model), grid_in.data_ptr(),
+                                          grid_out.data_ptr(), st.cuda_stream, C.byref(n)),
+                    "gcb_forward")
     if side:
       cur.wait_stream(self._step_stream)
     self.launches_per_step = int(n.value)
@@ -336,10 +343,11 @@ class Engine:
     grid_out = self.grid_out if grid_out is None else grid_out
     if planes_out.shape != (self.n_out, self.num_grid) or not planes_out.is_contiguous():
       raise ValueError("planes_out must be a contiguous [n_out, Ng] tensor")
-    _native.check(self._lib.gcb_unpack_grid_outputs(
-        grid_out.data_ptr(), 256, self.n_out, self.num_grid, self._ptr(scale), self._ptr(offset),
-        self._ptr(add_planes), self._ptr(add_plane_index), planes_out.data_ptr(), self._stream()),
-        "gcb_unpack_grid_outputs")
+    with self._on_device():
+      _native.check(self._lib.gcb_unpack_grid_outputs(
+          grid_out.data_ptr(), 256, self.n_out, self.num_grid, self._ptr(scale), self._ptr(offset),
+          self._ptr(add_planes), self._ptr(add_plane_index), planes_out.data_ptr(), self._stream()),
+          "gcb_unpack_grid_outputs")
     return planes_out
 
   def forward_features(self, grid_features: torch.Tensor) -> torch.Tensor:

@@ -137,12 +137,15 @@ class ChannelSlab:
   """One variable's place in the packed channel axis."""
 
   def __init__(self, name: str, start: int, stack_dims: Tuple[str, ...],
-               stack_sizes: Tuple[int, ...], var_dims: Tuple[str, ...]):
+               stack_sizes: Tuple[int, ...], var_dims: Tuple[str, ...],
+               stack_labels: Optional[Mapping[str, np.ndarray]] = None):
     self.name = name
     self.start = start
     self.stack_dims = stack_dims
     self.stack_sizes = stack_sizes
     self.var_dims = var_dims
+    # index labels of the stacked dims that have them (e.g. "level" -> pressure levels)
+    self.stack_labels = dict(stack_labels or {})
 
   @property
   def count(self) -> int:
@@ -163,7 +166,10 @@ def channel_layout(dataset: xs.Dataset, start: int = 0) -> List[ChannelSlab]:
     var = dataset.data_vars[name]
     stack_dims = tuple(d for d in var.dims if d not in _PRESERVED)
     stack_sizes = tuple(var.sizes[d] for d in stack_dims)
-    slab = ChannelSlab(name, offset, stack_dims, stack_sizes, var.dims)
+    labelled = dataset[name]          # with the Dataset's coordinates attached
+    labels = {d: labelled.index_labels(d) for d in stack_dims
+              if labelled.index_labels(d) is not None}
+    slab = ChannelSlab(name, offset, stack_dims, stack_sizes, var.dims, labels)
     slabs.append(slab)
     offset += slab.count
   return slabs

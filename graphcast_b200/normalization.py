@@ -64,22 +64,52 @@ def unnormalize(values: xs.Dataset, scales: xs.Dataset, locations: Optional[xs.D
   return values.map(one)
 
 
-def _per_channel(slab: model_utils.ChannelSlab, stats: Optional[xs.Dataset], default: float
-                 ) -> np.ndarray:
+_warned_missing = set()
+
+
+def _warn_missing_once(kind: str, name: str) -> None:
+  if (kind, name) not in _warned_missing:
+    _warned_missing.add((kind, name))
+    logging.warning("No normalization %s found for %s", kind, name)
+
+
+def _per_channel(slab: model_utils.ChannelSlab, stats: Optional[xs.Dataset], default: float,
+                 kind: str = "scale") -> np.ndarray:
   """Per-channel constant of one variable: stats[var] may be a scalar or vary
-  along stacked dims (e.g. "level"); it is broadcast over the slab's stack dims."""
+  along stacked dims (e.g. "level"); it is broadcast over the slab's stack dims.
+
+  Statistics are selected by LABEL along every labelled dim they share with the variable
+  (xarray's alignment, which the reference relies on: the released 37-level `*_by_level`
+  files serve 13-level models); a label of the variable that the statistics lack raises.
+  A variable without statistics keeps `default` and logs the reference's warning once."""
   out = np.full(slab.stack_sizes if slab.stack_sizes else (1,), default, np.float64)
-  if stats is not None and slab.name in stats:
-    v = stats.data_vars[slab.name]
-    bad = [d for d in v.dims if d not in slab.stack_dims]
-    if bad:
-      raise ValueError(f"normalisation statistics of {slab.name!r} vary along {bad}, "
-                       "which is not a channel dimension")
-    arr = np.asarray(v.values, np.float64)
-    shape = [v.sizes[d] if d in v.dims else 1 for d in slab.stack_dims] or [1]
-    arr = np.transpose(arr, [v.dims.index(d) for d in slab.stack_dims if d in v.dims]) \
-        if v.dims else arr
-    out = out * 0 + arr.reshape(shape)
+  if stats is None:
+    return out.reshape(-1)
+  if slab.name not in stats:
+    _warn_missing_once(kind, slab.name)
+    return out.reshape(-1)
+  v = stats[slab.name]                # with the statistics' coordinates attached
+  bad = [d for d in v.dims if d not in slab.stack_dims]
+  if bad:
+    raise ValueError(f"normalisation statistics of {slab.name!r} vary along {bad}, "
+                     "which is not a channel dimension")
+  for d in v.dims:
+    want, have = slab.stack_labels.get(d), v.index_labels(d)
+    size = slab.stack_sizes[slab.stack_dims.index(d)]
+    if want is not None and have is not None:
+      pos = {x.item(): i for i, x in enumerate(have)}
+      missing = [x.item() for x in want if x.item() not in pos]
+      if missing:
+        raise ValueError(f"normalisation statistics of {slab.name!r} lack {d} = {missing}")
+      v = v.isel({d: np.asarray([pos[x.item()] for x in want], np.int64)})
+    elif v.sizes[d] != size:
+      raise ValueError(f"normalisation statistics of {slab.name!r} have {v.sizes[d]} entries "
+                       f"along {d!r}, the data {size}, and no labels to align them by")
+  arr = np.asarray(v.values, np.float64)
+  shape = [v.sizes[d] if d in v.dims else 1 for d in slab.stack_dims] or [1]
+  arr = np.transpose(arr, [v.dims.index(d) for d in slab.stack_dims if d in v.dims]) \
+      if v.dims else arr
+  out = out * 0 + arr.reshape(shape)
   return out.reshape(-1)
 
 
@@ -103,9 +133,10 @@ class InputsAndResiduals(graphcast.Predictor):
       prediction = unnormalize(xs.Dataset({norm_prediction.name: norm_prediction}),
                                self._residual_scales, self._residual_locations
                                )[norm_prediction.name]
-      last_input = inputs[norm_prediction.name].isel(time=slice(-1, None))
-      return (prediction.transpose(*last_input.dims) + last_input).transpose(
-          *norm_prediction.dims)
+      # isel(time=-1) drops the time dim (reference :128-129), so the add broadcasts over the
+      # prediction's single time step instead of aligning two different time labels.
+      last_input = inputs[norm_prediction.name].isel(time=-1)
+      return prediction + last_input
     return unnormalize(xs.Dataset({norm_prediction.name: norm_prediction}),
                        self._scales, self._locations)[norm_prediction.name]
 
@@ -114,17 +145,20 @@ class InputsAndResiduals(graphcast.Predictor):
     in_slabs = model_utils.channel_layout(inputs)
     n_in = sum(s.count for s in in_slabs)
     f_slabs = model_utils.channel_layout(forcings, start=n_in)
-    key = (tuple((s.name, s.stack_sizes) for s in in_slabs + f_slabs),
-           tuple(sorted(targets_template.data_vars.keys())), str(device))
+    t_slabs = model_utils.channel_layout(targets_template)
+    sig = lambda s: (s.name, s.stack_dims, s.stack_sizes,
+                     tuple((d, v.tobytes()) for d, v in sorted(s.stack_labels.items())))
+    key = (tuple(sig(s) for s in in_slabs + f_slabs), tuple(sig(s) for s in t_slabs), str(device))
     if self._fused_cache is not None and self._fused_cache[0] == key:
       return self._fused_cache[1]
-    mean = np.concatenate([_per_channel(s, self._locations, 0.0) for s in in_slabs + f_slabs])
+    mean = np.concatenate([_per_channel(s, self._locations, 0.0, "location")
+                           for s in in_slabs + f_slabs])
     scale = np.concatenate([_per_channel(s, self._scales, 1.0) for s in in_slabs + f_slabs])
-    t_slabs = model_utils.channel_layout(targets_template)
     out_scale, out_offset, add_idx = [], [], []
     in_by_name = {s.name: s for s in in_slabs}
     for s in t_slabs:
-      if s.stack_dims and s.stack_dims[0] == "time" and s.stack_sizes[0] != 1:
+      # reference :114-117: `norm_prediction.sizes.get("time") != 1` raises (also without a time dim)
+      if "time" not in s.stack_dims or s.stack_sizes[s.stack_dims.index("time")] != 1:
         raise ValueError("normalization.InputsAndResiduals only supports predicting a "
                          "single timestep.")
       if s.name in in_by_name:
@@ -141,7 +175,7 @@ class InputsAndResiduals(graphcast.Predictor):
         add_idx.append(src.start + (n_time - 1) * per_frame + np.arange(s.count))
       else:
         out_scale.append(_per_channel(s, self._scales, 1.0))
-        out_offset.append(_per_channel(s, self._locations, 0.0))
+        out_offset.append(_per_channel(s, self._locations, 0.0, "location"))
         add_idx.append(np.full([s.count], -1))
     t = lambda a, dt: torch.as_tensor(np.concatenate(a) if isinstance(a, list) else a).to(dt).to(device)
     consts = graphcast.FusedNormalization(

@@ -138,7 +138,39 @@ class DataArray:
     return out
 
   # -- dims-aware arithmetic ---------------------------------------------------
+  def index_labels(self, dim: str) -> Optional[np.ndarray]:
+    """Labels of `dim` (its 1-d index coordinate), or None when the dim is unlabelled."""
+    c = self.coords.get(dim)
+    if c is not None and c[0] == (dim,) and c[1].shape[0] == self.sizes.get(dim, -1):
+      return c[1]
+    return None
+
   def _binary(self, other, op):
+    if isinstance(other, DataArray):
+      # Label alignment like xarray's arithmetic (inner join on every shared, labelled
+      # dim): the released 37-level `*_by_level` statistics must combine with 13-level
+      # inputs by pressure level, not by position (reference normalization.py:29-70
+      # relies on this).
+      lhs, rhs = self, other
+      for d in self.dims:
+        if d not in other.dims:
+          continue
+        la, lb = self.index_labels(d), other.index_labels(d)
+        if la is None or lb is None:
+          continue
+        if la.shape == lb.shape and np.array_equal(la, lb):
+          continue
+        pos_b = {v.item() if hasattr(v, "item") else v: i for i, v in enumerate(lb)}
+        keep_a = [i for i, v in enumerate(la) if (v.item() if hasattr(v, "item") else v) in pos_b]
+        keep_b = [pos_b[(la[i].item() if hasattr(la[i], "item") else la[i])] for i in keep_a]
+        lhs = lhs.isel({d: np.asarray(keep_a, np.int64)})
+        rhs = rhs.isel({d: np.asarray(keep_b, np.int64)})
+      if lhs is not self or rhs is not other:
+        return lhs._binary_aligned(rhs, op)
+      return self._binary_aligned(other, op)
+    return DataArray(op(self.data, other), self.dims, dict(self.coords), self.name)
+
+  def _binary_aligned(self, other, op):
     if isinstance(other, DataArray):
       out_dims = list(self.dims) + [d for d in other.dims if d not in self.dims]
       a = _broadcast_to_dims(self, out_dims)

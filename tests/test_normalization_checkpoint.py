@@ -146,3 +146,50 @@ def test_checkpoint_written_by_the_reference_loads_and_round_trips():
   assert set(mine.files) == set(ref.files)
   for k in ref.files:
     np.testing.assert_array_equal(mine[k], ref[k])
+
+
+def test_statistics_are_aligned_by_pressure_level_not_by_position():
+  """The released `*_by_level` statistics have 37 levels and serve the 13-level models: the
+  reference gets the right rows through xarray's label alignment (normalization.py:29-70)."""
+  task13 = graphcast.TASK_13_PRECIP_OUT
+  inputs, template, forcings = synthetic.make_example(task13, 30.0, seed=1)
+  assert inputs["temperature"].index_labels("level") is not None
+  std37, mean37, dstd37 = (_stats(graphcast.TASK, s) for s in (1, 2, 3))
+  lv37 = list(graphcast.TASK.pressure_levels)
+  pick = np.asarray([lv37.index(l) for l in task13.pressure_levels])
+  sel = lambda ds: xs.Dataset(
+      {k: (v.isel(level=pick) if "level" in v.dims else v) for k, v in ds.data_vars.items()},
+      coords={"level": np.asarray(task13.pressure_levels)})
+  std13, mean13, dstd13 = sel(std37), sel(mean37), sel(dstd37)
+  # generic path
+  a, b = Echo(), Echo()
+  out37 = normalization.InputsAndResiduals(a, std37, mean37, dstd37)(inputs, template, forcings)
+  out13 = normalization.InputsAndResiduals(b, std13, mean13, dstd13)(inputs, template, forcings)
+  for name in ("temperature", "geopotential"):
+    assert a.inputs.data_vars[name].shape == inputs.data_vars[name].shape
+    np.testing.assert_array_equal(a.inputs.data_vars[name].values, b.inputs.data_vars[name].values)
+    np.testing.assert_array_equal(out37.data_vars[name].values, out13.data_vars[name].values)
+  # fused per-channel constants
+  c37 = normalization.InputsAndResiduals(Echo(), std37, mean37, dstd37)._fused_constants(
+      inputs, template, forcings, torch.device("cpu"))
+  c13 = normalization.InputsAndResiduals(Echo(), std13, mean13, dstd13)._fused_constants(
+      inputs, template, forcings, torch.device("cpu"))
+  for f in ("in_mean", "in_scale", "out_scale", "out_offset"):
+    np.testing.assert_array_equal(getattr(c37, f).numpy(), getattr(c13, f).numpy())
+  # a level the statistics do not have is an error, not a silent misalignment
+  bad = xs.Dataset({k: (v.isel(level=np.arange(12)) if "level" in v.dims else v)
+                    for k, v in std13.data_vars.items()},
+                   coords={"level": np.asarray(task13.pressure_levels[:12])})
+  with pytest.raises(ValueError, match="lack level"):
+    normalization.InputsAndResiduals(Echo(), bad, mean13, dstd13)._fused_constants(
+        inputs, template, forcings, torch.device("cpu"))
+
+
+def test_fused_path_rejects_targets_without_a_single_time_step():
+  task = graphcast.TASK_13_PRECIP_OUT
+  inputs, template, forcings = synthetic.make_example(task, 30.0, seed=1)
+  std, mean, dstd = _stats(task, 1), _stats(task, 2), _stats(task, 3)
+  no_time = xs.Dataset({k: v.isel(time=0) for k, v in template.data_vars.items()})
+  with pytest.raises(ValueError, match="single timestep"):
+    normalization.InputsAndResiduals(Echo(), std, mean, dstd)._fused_constants(
+        inputs, no_time, forcings, torch.device("cpu"))
