@@ -13,7 +13,7 @@ import os
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)),
                          "libgraphcast_b200.so")
 
-GCB_ABI_VERSION = 1
+GCB_ABI_VERSION = 2
 GCB_MAX_MSG_STEPS = 64
 PREC_BF16X3, PREC_BF16, PREC_FP32_SIMT = 0, 1, 2
 PRECISIONS = {"bf16x3": PREC_BF16X3, "bf16": PREC_BF16, "fp32_simt": PREC_FP32_SIMT}
@@ -78,7 +78,32 @@ class Model(C.Structure):
       ("hidden", _fp), ("edge_a_img", _fp), ("edge_b", _fp), ("mesh_in_img", _fp), ("grid_lat", _fp), ("grid_lat_img", _fp), ("mesh_lat", _fp),
       ("mesh_lat_img", _fp), ("mesh_agg", _fp), ("mesh_agg_img", _fp), ("mesh_edge", _fp),
       ("mesh_edge_img", _fp), ("mesh_msg", _fp), ("grid_agg_img", _fp),
+      ("fuse", C.c_int32), ("chain_lag", C.c_int32),
+      ("num_grid_owned", C.c_int32), ("num_mesh_owned", C.c_int32),
+      ("chain_scratch", _fp),
+      ("image_residual", C.c_int32), ("pad_", C.c_int32),
   ]
+
+
+GCB_MAX_CHAIN = 4
+STAGE_ENCODE, STAGE_PROCESS_EMBED, STAGE_PROCESS_STEP, STAGE_DECODE = 0, 1, 2, 3
+
+
+class ChainLayer(C.Structure):
+  _fields_ = [("nseg", C.c_int32), ("seg", Segment * 3), ("seg_from", C.c_int32 * 3),
+              ("w_packed", _fp), ("bias", _fp), ("ln_scale", _fp), ("ln_offset", _fp),
+              ("act", C.c_int32), ("keep", C.c_int32),
+              ("residual", _fp), ("ld_res", C.c_int32),
+              ("residual_img", _fp),
+              ("out", _fp), ("ld_out", C.c_int32),
+              ("out_y", _fp), ("ld_out_y", C.c_int32),
+              ("out_img", _fp),
+              ("n_pre_add", C.c_int32), ("pre_add", PreAdd * 2)]
+
+
+class ChainDesc(C.Structure):
+  _fields_ = [("rows", C.c_int32), ("nlayers", C.c_int32), ("precision", C.c_int32),
+              ("lag", C.c_int32), ("scratch", _fp), ("layer", ChainLayer * GCB_MAX_CHAIN)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/graphcast_b200.h.
@@ -101,6 +126,10 @@ EXPORTS = {
     "gcb_unpack_grid_outputs": (C.c_int, [_fp, C.c_int32, C.c_int32, C.c_int64, _fp, _fp, _fp,
                                           _fp, _fp, _fp]),
     "gcb_forward": (C.c_int, [C.POINTER(Model), _fp, _fp, _fp, C.POINTER(C.c_int32)]),
+    "gcb_forward_stage": (C.c_int, [C.POINTER(Model), C.c_int32, C.c_int32, _fp, _fp, _fp,
+                                    C.POINTER(C.c_int32)]),
+    "gcb_chain_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "gcb_chain_forward": (C.c_int, [C.POINTER(ChainDesc), _fp]),
     "gcb_set_cluster_size": (C.c_int, [C.c_int32]),
     "gcb_toa_incident_solar_radiation": (C.c_int, [_fp, C.c_int32, C.c_int32, _fp, _fp, _fp, _fp,
                                          C.c_int32, C.c_int32, _fp, _fp]),

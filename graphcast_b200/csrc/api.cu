@@ -12,6 +12,7 @@
 #include "aux_kernels.cuh"
 #include "mlp_simt.cuh"
 #include "mlp_tc.cuh"
+#include "mlp_chain.cuh"
 
 namespace {
 
@@ -225,6 +226,124 @@ int launch_simt(const gcb_layer_desc& d, cudaStream_t stream) {
   return GCB_OK;
 }
 
+// ---- fused layer chains (mlp_chain.cuh) -----------------------------------------------
+struct ChainShape {
+  int nq = 0;          // kept layers (scratch rings)
+  int maxdist = 1;     // largest (consumer layer - producer layer)
+  int nslots = 2;
+  bool pre = false;
+};
+
+int validate_chain(const gcb_chain_desc* d, ChainShape* shape) {
+  GCB_CHECK_ARG(d != nullptr, "null descriptor");
+  GCB_CHECK_ARG(d->rows >= 0, "rows < 0");
+  GCB_CHECK_ARG(d->nlayers >= 1 && d->nlayers <= GCB_MAX_CHAIN, "nlayers must be 1..GCB_MAX_CHAIN");
+  GCB_CHECK_ARG(d->precision == GCB_PREC_BF16X3 || d->precision == GCB_PREC_BF16,
+                "chains run on the tensor-core path only (BF16X3 / BF16)");
+  GCB_CHECK_ARG(d->lag >= 0 && d->lag <= 2, "lag must be 0 (default), 1 or 2");
+  ChainShape sh;
+  int vecs = 0;
+  for (int l = 0; l < d->nlayers; ++l) {
+    const gcb_chain_layer& g = d->layer[l];
+    GCB_CHECK_ARG(g.nseg >= 1 && g.nseg <= 3, "nseg must be 1..3");
+    for (int s = 0; s < g.nseg; ++s) {
+      const int from = g.seg_from[s];
+      if (from >= 0) {
+        GCB_CHECK_ARG(from < l && d->layer[from].keep, "seg_from must name an earlier layer with keep = 1");
+        if (l - from > sh.maxdist) sh.maxdist = l - from;
+        continue;
+      }
+      const gcb_segment& sg = g.seg[s];
+      GCB_CHECK_ARG(sg.k > 0 && sg.k % 16 == 0, "segment k must be a positive multiple of 16");
+      if (sg.img != nullptr) {
+        GCB_CHECK_ARG(aligned16(sg.img), "segment image unaligned");
+        continue;
+      }
+      GCB_CHECK_ARG(sg.table != nullptr && aligned16(sg.table), "segment table null/unaligned");
+      GCB_CHECK_ARG(sg.k_valid > 0 && sg.k_valid <= sg.k && sg.k_valid % 4 == 0,
+                    "segment k_valid must be a multiple of 4 and <= k");
+      GCB_CHECK_ARG(sg.ld % 4 == 0 && sg.ld >= sg.k_valid, "segment ld must be a multiple of 4 and >= k_valid");
+      GCB_CHECK_ARG(sg.fan >= 1, "segment fan must be >= 1");
+    }
+    GCB_CHECK_ARG(g.w_packed != nullptr && aligned16(g.w_packed), "w_packed null/unaligned");
+    GCB_CHECK_ARG((g.ln_scale == nullptr) == (g.ln_offset == nullptr), "ln_scale/ln_offset mismatch");
+    GCB_CHECK_ARG(g.act == GCB_ACT_NONE || g.act == GCB_ACT_SWISH, "unknown activation");
+    GCB_CHECK_ARG(!(g.act == GCB_ACT_SWISH && g.ln_scale != nullptr),
+                  "a chain layer is swish OR LayerNorm, not both");
+    GCB_CHECK_ARG(g.out || g.out_y || g.out_img || g.keep, "layer has no output");
+    if (g.act == GCB_ACT_SWISH)
+      GCB_CHECK_ARG(!g.out && !g.out_y && !g.residual,
+                    "a swish chain layer delivers operand images only (out_img / keep)");
+    if (g.ln_scale == nullptr)
+      GCB_CHECK_ARG(!g.residual && !g.residual_img, "residual needs a LayerNorm layer in a chain");
+    if (g.residual_img)
+      GCB_CHECK_ARG(aligned16(g.residual_img) && !g.residual && !g.out,
+                    "residual_img excludes residual and out");
+    if (g.out) GCB_CHECK_ARG(aligned16(g.out) && g.ld_out % 4 == 0 && g.ld_out >= 512, "out unaligned");
+    if (g.out_y) GCB_CHECK_ARG(aligned16(g.out_y) && g.ld_out_y % 4 == 0 && g.ld_out_y >= 512, "out_y unaligned");
+    if (g.out_img) GCB_CHECK_ARG(aligned16(g.out_img), "out_img unaligned");
+    if (g.residual) GCB_CHECK_ARG(aligned16(g.residual) && g.ld_res % 4 == 0 && g.ld_res >= 512, "residual unaligned");
+    GCB_CHECK_ARG(g.n_pre_add >= 0 && g.n_pre_add <= 2, "n_pre_add must be 0..2");
+    if (g.n_pre_add > 0) {
+      GCB_CHECK_ARG(g.ln_scale == nullptr, "pre_add cannot be combined with LayerNorm");
+      for (int i = 0; i < g.n_pre_add; ++i)
+        GCB_CHECK_ARG(g.pre_add[i].table != nullptr && aligned16(g.pre_add[i].table) &&
+                          g.pre_add[i].ld % 4 == 0 && g.pre_add[i].ld >= 512,
+                      "pre_add table null/unaligned");
+      sh.pre = true;
+    }
+    vecs += (g.bias ? 1 : 0) + (g.ln_scale ? 2 : 0);
+    if (g.keep) ++sh.nq;
+  }
+  GCB_CHECK_ARG(vecs <= gcb::kChainParamVecs, "too many bias / LayerNorm vectors for one chain");
+  const int lag = d->lag > 0 ? d->lag : 1;
+  sh.nslots = lag * sh.maxdist + 1;
+  GCB_CHECK_ARG(sh.nslots <= gcb::kChainSlotsMax, "lag x distance too large");
+  if (sh.nq > 0) GCB_CHECK_ARG(d->scratch != nullptr && aligned16(d->scratch), "scratch null/unaligned");
+  *shape = sh;
+  return GCB_OK;
+}
+
+template <bool kSplit, bool kPre>
+int launch_chain_variant(const gcb_chain_desc& d, const ChainShape& sh, cudaStream_t stream) {
+  using Cfg = gcb::ChainConfig<kSplit, kPre>;
+  auto kernel = gcb::mlp_chain_tc_kernel<kSplit, kPre>;
+  static bool attr_set[64] = {false};
+  static int max_clusters[64] = {0};
+  int dev = 0;
+  GCB_CUDA(cudaGetDevice(&dev));
+  GCB_CHECK_ARG(dev >= 0 && dev < 64, "device index out of range");
+  if (!attr_set[dev]) {
+    GCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set[dev] = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(gcb::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters[dev] == 0) {
+    cfg.gridDim = dim3(sm_count_cached() / 2 * 2);
+    int nc = 0;
+    GCB_CUDA(cudaOccupancyMaxActiveClusters(&nc, kernel, &cfg));
+    if (nc <= 0) return fail(GCB_ERR_CUDA, "no resident cluster fits on this device");
+    if (nc > sm_count_cached() / 2) nc = sm_count_cached() / 2;   // the scratch is sized for SMs / 2
+    max_clusters[dev] = nc;
+  }
+  const int tiles = (d.rows + gcb::kTileM - 1) / gcb::kTileM;
+  int clusters = tiles < max_clusters[dev] ? tiles : max_clusters[dev];
+  cfg.gridDim = dim3(clusters * 2);
+  GCB_CUDA(cudaLaunchKernelEx(&cfg, kernel, d, sh.nq, sh.nslots));
+  return GCB_OK;
+}
+
 struct StepCtx {
   const gcb_model* m;
   cudaStream_t stream;
@@ -246,6 +365,7 @@ gcb_segment seg_img(const void* img, int k) {
 }
 
 struct MlpOut {
+  const void* residual_img = nullptr;   // residual as an operand image (fused path only)
   const float* residual = nullptr;   // fp32 [rows,512], added to the result
   float* out = nullptr;              // residual + y (fp32)
   int ld_out = 512;
@@ -253,19 +373,48 @@ struct MlpOut {
   void* out_img = nullptr;           // residual + y as an operand image
 };
 
-// Two-layer MLP: hidden = swish(concat(segs) @ W0 + b0 [+ gathered addends]) as an operand
-// image;  y = [LN](hidden @ W1 + b1), delivered as MlpOut says.
+// Two-layer MLP: hidden = swish(concat(segs) @ W0 + b0 [+ gathered addends]);
+// y = [LN](hidden @ W1 + b1), delivered as MlpOut says.  Fused (gcb_model.fuse, tensor-core
+// precisions, n1 = 512): ONE chain launch, the hidden activation stays in the L2-resident
+// scratch.  Otherwise two launches with the hidden activation as an operand image in HBM.
 int run_mlp(StepCtx& c, const gcb_mlp& w, int rows, int nseg, const gcb_segment* segs,
             const MlpOut& o, const void* w0_packed_override = nullptr,
             const float* w0_f32_override = nullptr, int n_pre = 0, const gcb_pre_add* pre = nullptr) {
   if (rows == 0) return GCB_OK;
+  int k0 = 0;
+  for (int s = 0; s < nseg; ++s) k0 += segs[s].k;
+  if (w0_packed_override == nullptr && k0 != w.k0)
+    return fail(GCB_ERR_INVALID, "run_mlp: segment widths do not match the weight");
+  if (c.m->fuse && c.m->precision != GCB_PREC_FP32_SIMT && w.n1 == 512 && w.n1_valid == 512 &&
+      o.ld_out == 512) {
+    gcb_chain_desc ch;
+    memset(&ch, 0, sizeof(ch));
+    ch.rows = rows; ch.nlayers = 2; ch.precision = c.m->precision; ch.lag = c.m->chain_lag;
+    ch.scratch = c.m->chain_scratch;
+    gcb_chain_layer& a = ch.layer[0];
+    a.nseg = nseg;
+    for (int s = 0; s < nseg; ++s) { a.seg[s] = segs[s]; a.seg_from[s] = -1; }
+    a.w_packed = w0_packed_override ? w0_packed_override : w.w0_packed;
+    a.bias = w.b0; a.act = GCB_ACT_SWISH; a.keep = 1;
+    a.n_pre_add = n_pre;
+    for (int i = 0; i < n_pre; ++i) a.pre_add[i] = pre[i];
+    gcb_chain_layer& b = ch.layer[1];
+    b.nseg = 1; b.seg_from[0] = 0; b.seg[0].k = 512; b.seg_from[1] = b.seg_from[2] = -1;
+    b.w_packed = w.w1_packed; b.bias = w.b1; b.ln_scale = w.ln_scale; b.ln_offset = w.ln_offset;
+    b.act = GCB_ACT_NONE;
+    b.residual = o.residual; b.ld_res = 512; b.residual_img = o.residual_img;
+    b.out = o.out; b.ld_out = 512; b.out_y = o.out_y; b.ld_out_y = 512; b.out_img = o.out_img;
+    int rc = gcb_chain_forward(&ch, c.stream);
+    if (rc) return rc;
+    c.launches += 1;
+    return GCB_OK;
+  }
+  if (o.residual_img != nullptr)
+    return fail(GCB_ERR_INVALID, "run_mlp: an image residual needs the fused path");
   gcb_layer_desc l0;
   memset(&l0, 0, sizeof(l0));
   l0.rows = rows; l0.n = 512; l0.n_valid = 512; l0.nseg = nseg;
-  int k0 = 0;
-  for (int s = 0; s < nseg; ++s) { l0.seg[s] = segs[s]; k0 += segs[s].k; }
-  if (w0_packed_override == nullptr && k0 != w.k0)
-    return fail(GCB_ERR_INVALID, "run_mlp: segment widths do not match the weight");
+  for (int s = 0; s < nseg; ++s) l0.seg[s] = segs[s];
   l0.w_packed = w0_packed_override ? w0_packed_override : w.w0_packed;
   l0.w_f32 = w0_packed_override ? w0_f32_override : w.w0_f32;
   l0.bias = w.b0;
@@ -424,6 +573,53 @@ int gcb_layer_forward(const gcb_layer_desc* d, void* stream) {
   }
 }
 
+int64_t gcb_chain_scratch_bytes(int32_t device, int32_t n_keep_layers, int32_t lag,
+                                int32_t max_distance) {
+  if (n_keep_layers < 0 || n_keep_layers > GCB_MAX_CHAIN || lag < 0 || lag > 2 || max_distance < 1)
+    return -1;
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0)
+    return -1;
+  const int nslots = (lag > 0 ? lag : 1) * max_distance + 1;
+  if (nslots > gcb::kChainSlotsMax) return -1;
+  return static_cast<int64_t>(sms / 2) * n_keep_layers * nslots * gcb::kScratchTileBytes;
+}
+
+int gcb_chain_forward(const gcb_chain_desc* d, void* stream) {
+  ChainShape sh;
+  int rc = validate_chain(d, &sh);
+  if (rc) return rc;
+  if (d->rows == 0) return GCB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // Algorithmic work of the launch: 2*rows*K*n flops per layer; bytes = external A operands
+  // (incl. gathers) + gathered addends + weights + residual + outputs; results handed over
+  // inside the chain are not HBM traffic.
+  double flops = 0, bytes = 0;
+  const double rows = d->rows;
+  for (int l = 0; l < d->nlayers; ++l) {
+    const gcb_chain_layer& g = d->layer[l];
+    double kv = 0, a_elems = 0;
+    for (int s = 0; s < g.nseg; ++s) {
+      if (g.seg_from[s] >= 0) { kv += 512; continue; }
+      const double w = g.seg[s].img ? g.seg[s].k : g.seg[s].k_valid;
+      kv += w;
+      a_elems += w * (g.seg[s].img ? 1 : g.seg[s].fan);
+    }
+    a_elems += 512.0 * g.n_pre_add;
+    flops += 2.0 * rows * kv * 512;
+    bytes += 4.0 * (rows * a_elems + kv * 512 +
+                    rows * 512 * ((g.out ? 1 : 0) + (g.out_y ? 1 : 0) + (g.residual ? 1 : 0) +
+                                  (g.out_img ? 1 : 0)));
+    // (a residual_img that is also a segment of the chain is read from HBM once: not counted again)
+  }
+  ProfScope prof(st, GCB_KIND_CHAIN_TC, flops, bytes);
+  const bool split = d->precision == GCB_PREC_BF16X3;
+  if (split) return sh.pre ? launch_chain_variant<true, true>(*d, sh, st)
+                           : launch_chain_variant<true, false>(*d, sh, st);
+  return sh.pre ? launch_chain_variant<false, true>(*d, sh, st)
+                : launch_chain_variant<false, false>(*d, sh, st);
+}
+
 int gcb_segment_sum(const float* msg, int32_t ld_msg, const int32_t* row_ptr, int32_t num_nodes,
                     float* out, int32_t ld_out, int32_t width, void* stream) {
   return gcb_segment_sum_heavy(msg, ld_msg, row_ptr, num_nodes, nullptr, 0, out, ld_out, width, stream);
@@ -432,21 +628,21 @@ int gcb_segment_sum(const float* msg, int32_t ld_msg, const int32_t* row_ptr, in
 namespace {
 int segment_sum_launch(const float* msg, int32_t ld_msg, const int32_t* row_ptr, int32_t num_nodes,
                        const int32_t* heavy, int32_t num_heavy, float* out, int32_t ld_out,
-                       int32_t width, void* img, void* stream);
+                       int32_t width, void* img, long long num_edges, void* stream);
 }
 
 int gcb_segment_sum_heavy(const float* msg, int32_t ld_msg, const int32_t* row_ptr,
                           int32_t num_nodes, const int32_t* heavy, int32_t num_heavy, float* out,
                           int32_t ld_out, int32_t width, void* stream) {
   return segment_sum_launch(msg, ld_msg, row_ptr, num_nodes, heavy, num_heavy, out, ld_out, width,
-                            nullptr, stream);
+                            nullptr, 0, stream);
 }
 
 namespace {
 // img (optional): operand image of the [num_nodes, 512] result, written by the same kernel.
 int segment_sum_launch(const float* msg, int32_t ld_msg, const int32_t* row_ptr, int32_t num_nodes,
                        const int32_t* heavy, int32_t num_heavy, float* out, int32_t ld_out,
-                       int32_t width, void* img, void* stream) {
+                       int32_t width, void* img, long long num_edges, void* stream) {
   GCB_CHECK_ARG(msg && row_ptr && out, "null pointer");
   GCB_CHECK_ARG(num_heavy >= 0 && (num_heavy == 0 || heavy != nullptr), "heavy list is null");
   GCB_CHECK_ARG(width == 512, "segment_sum supports width 512");
@@ -456,8 +652,9 @@ int segment_sum_launch(const float* msg, int32_t ld_msg, const int32_t* row_ptr,
   long long blocks = (static_cast<long long>(num_nodes) + warps_per_block - 1) / warps_per_block;
   const long long cap = static_cast<long long>(sm_count_cached()) * 16;
   if (blocks > cap) blocks = cap;
+  // algorithmic bytes: every message row read once, every node row written once (+ its image)
   ProfScope prof(static_cast<cudaStream_t>(stream), GCB_KIND_SEGMENT_SUM, 0.0,
-                 4.0 * width * (static_cast<double>(num_nodes) + 0.0) + 0.0);
+                 4.0 * width * (static_cast<double>(num_edges) + num_nodes * (img ? 2.0 : 1.0)));
   gcb::segment_sum_kernel<4><<<static_cast<int>(blocks) + num_heavy, 256, 0,
                               static_cast<cudaStream_t>(stream)>>>(
       msg, ld_msg, row_ptr, num_nodes, out, ld_out, heavy, num_heavy,
@@ -667,10 +864,8 @@ int gcb_forward(const gcb_model* m, const void* grid_in_img, float* grid_out, vo
 
 namespace {
 
-int forward_eager(const gcb_model* m, const void* grid_in_img, float* grid_out, void* stream,
-                  int32_t* launches) {
+int check_model(const gcb_model* m) {
   GCB_CHECK_ARG(m->msg_steps >= 1 && m->msg_steps <= GCB_MAX_MSG_STEPS, "msg_steps out of range");
-  GCB_CHECK_ARG(m->e_m2g == 3 * m->num_grid, "mesh2grid must have fan-in 3");
   GCB_CHECK_ARG(m->hidden && m->edge_a_img && m->edge_b && m->mesh_in_img &&
                     m->grid_lat && m->grid_lat_img && m->mesh_lat && m->mesh_lat_img &&
                     m->mesh_agg && m->mesh_agg_img && m->mesh_edge && m->mesh_edge_img &&
@@ -679,20 +874,51 @@ int forward_eager(const gcb_model* m, const void* grid_in_img, float* grid_out, 
   if (m->pregather)
     GCB_CHECK_ARG(m->zero_bias && m->proj_grid && m->proj_mesh_a && m->proj_mesh_b,
                   "pregather needs zero_bias and the proj_* buffers");
-  StepCtx c{m, static_cast<cudaStream_t>(stream), 0};
+  if (m->fuse) GCB_CHECK_ARG(m->chain_scratch != nullptr, "fuse needs chain_scratch");
+  GCB_CHECK_ARG(m->num_grid_owned >= 0 && m->num_grid_owned <= m->num_grid &&
+                    m->num_mesh_owned >= 0 && m->num_mesh_owned <= m->num_mesh,
+                "owned row counts out of range");
+  return GCB_OK;
+}
+
+// Latent streams as images only (gcb_model.image_residual)?
+bool img_only(const gcb_model* m) {
+  return m->image_residual && m->fuse && m->pregather && m->precision != GCB_PREC_FP32_SIMT;
+}
+// Output of an MLP that CREATES a latent stream (master + image, or image only).
+MlpOut latent_new(const gcb_model* m, float* master, void* img) {
+  MlpOut o;
+  o.out_img = img;
+  if (!img_only(m)) o.out = master;
+  return o;
+}
+// Output of an MLP that UPDATES a latent stream in place: x += y.
+MlpOut latent_update(const gcb_model* m, float* master, void* img) {
+  MlpOut o;
+  o.out_img = img;
+  if (img_only(m)) { o.residual_img = img; }
+  else { o.residual = master; o.out = master; }
+  return o;
+}
+
+// Rows that node updates cover: all of them, or the owned prefix of a partition's local table.
+int grid_rows(const gcb_model* m) { return m->num_grid_owned > 0 ? m->num_grid_owned : m->num_grid; }
+int mesh_rows(const gcb_model* m) { return m->num_mesh_owned > 0 ? m->num_mesh_owned : m->num_mesh; }
+
+// ---------------- encoder: grid2mesh_gnn (graphcast.py:550-604) ----------------
+int stage_encode(StepCtx& c, const void* grid_in_img) {
+  const gcb_model* m = c.m;
   int rc;
   gcb_segment s[3];
   const int D = 512;
   MlpOut o;
-
-  // ---------------- encoder: grid2mesh_gnn (graphcast.py:550-604) ----------------
   // vg0 = LN.MLP(grid_in)  -> grid_lat (+ image)
   s[0] = seg_img(grid_in_img, m->c_in_pad);
-  o = MlpOut(); o.out = m->grid_lat; o.out_img = m->grid_lat_img;
+  o = latent_new(m, m->grid_lat, m->grid_lat_img);
   if ((rc = run_mlp(c, m->enc_grid, m->num_grid, 1, s, o))) return rc;
   // vm0 = LN.MLP(mesh_in)  -> mesh_lat (+ image)
   s[0] = seg_img(m->mesh_in_img, m->c_in_pad);
-  o = MlpOut(); o.out = m->mesh_lat; o.out_img = m->mesh_lat_img;
+  o = latent_new(m, m->mesh_lat, m->mesh_lat_img);
   if ((rc = run_mlp(c, m->enc_mesh, m->num_mesh, 1, s, o))) return rc;
   // e1 = LN.MLP(g2m edge feats)  -> image only (its fp32 form is never needed)
   s[0] = seg(m->g2m_feat, nullptr, 4, 16, 4);
@@ -702,73 +928,127 @@ int forward_eager(const gcb_model* m, const void* grid_in_img, float* grid_out, 
   o = MlpOut(); o.out = m->edge_b;
   if ((rc = run_edge_mlp(c, m->proc_e_g2m, &m->proc_e_g2m_split, m->e_g2m, m->edge_a_img,
                          m->grid_lat, m->grid_lat_img, m->num_grid, m->g2m_snd, m->proj_grid,
-                         m->mesh_lat, m->mesh_lat_img, m->num_mesh, m->g2m_rcv, m->proj_mesh_a, o)))
+                         m->mesh_lat, m->mesh_lat_img, mesh_rows(m), m->g2m_rcv, m->proj_mesh_a, o)))
     return rc;
   // agg1 = segment_sum(m1)
-  if ((rc = segment_sum_launch(m->edge_b, D, m->g2m_row_ptr, m->num_mesh, m->g2m_heavy,
-                               m->n_g2m_heavy, m->mesh_agg, D, D, m->mesh_agg_img, stream))) return rc;
+  if ((rc = segment_sum_launch(m->edge_b, D, m->g2m_row_ptr, mesh_rows(m), m->g2m_heavy,
+                               m->n_g2m_heavy, m->mesh_agg, D, D, m->mesh_agg_img, m->e_g2m,
+                               c.stream))) return rc;
   c.launches += 1;
   // vm1 = vm0 + LN.MLP([vm0 | agg1])  (in place)
   s[0] = seg_img(m->mesh_lat_img, D);
   s[1] = seg_img(m->mesh_agg_img, D);
-  o = MlpOut(); o.residual = m->mesh_lat; o.out = m->mesh_lat; o.out_img = m->mesh_lat_img;
-  if ((rc = run_mlp(c, m->proc_n_mesh_g2m, m->num_mesh, 2, s, o))) return rc;
+  o = latent_update(m, m->mesh_lat, m->mesh_lat_img);
+  if ((rc = run_mlp(c, m->proc_n_mesh_g2m, mesh_rows(m), 2, s, o))) return rc;
   // vg1 = vg0 + LN.MLP([vg0])  (in place; grid nodes receive nothing in grid2mesh)
   s[0] = seg_img(m->grid_lat_img, D);
-  o = MlpOut(); o.residual = m->grid_lat; o.out = m->grid_lat; o.out_img = m->grid_lat_img;
-  if ((rc = run_mlp(c, m->proc_n_grid_g2m, m->num_grid, 1, s, o))) return rc;
+  o = latent_update(m, m->grid_lat, m->grid_lat_img);
+  return run_mlp(c, m->proc_n_grid_g2m, grid_rows(m), 1, s, o);
+}
 
-  // ---------------- processor: mesh_gnn (graphcast.py:606-639) --------------------
+// ---------------- processor: mesh_gnn (graphcast.py:606-639) --------------------
+int stage_process_embed(StepCtx& c) {
+  const gcb_model* m = c.m;
+  gcb_segment s[3];
   s[0] = seg(m->mesh_feat, nullptr, 4, 16, 4);
-  o = MlpOut(); o.out = m->mesh_edge; o.out_img = m->mesh_edge_img;
-  if ((rc = run_mlp(c, m->enc_e_mesh, m->e_mesh, 1, s, o))) return rc;
-  for (int k = 0; k < m->msg_steps; ++k) {
-    const bool last = (k == m->msg_steps - 1);
-    // m = LN.MLP([e | v[snd] | v[rcv]]) -> mesh_msg;  e += m (skipped on the last step: the
-    // updated edge latents are never read again).
-    o = MlpOut(); o.out_y = m->mesh_msg;
-    if (!last) { o.residual = m->mesh_edge; o.out = m->mesh_edge; o.out_img = m->mesh_edge_img; }
-    if ((rc = run_edge_mlp(c, m->proc_e_mesh[k], &m->proc_e_mesh_split[k], m->e_mesh, m->mesh_edge_img,
-                           m->mesh_lat, m->mesh_lat_img, m->num_mesh, m->mesh_snd, m->proj_mesh_a,
-                           m->mesh_lat, m->mesh_lat_img, m->num_mesh, m->mesh_rcv, m->proj_mesh_b, o)))
-      return rc;
-    if ((rc = segment_sum_launch(m->mesh_msg, D, m->mesh_row_ptr, m->num_mesh, nullptr, 0, m->mesh_agg,
-                                 D, D, m->mesh_agg_img, stream))) return rc;
-    c.launches += 1;
-    // v += LN.MLP([v | agg])
-    s[0] = seg_img(m->mesh_lat_img, D);
-    s[1] = seg_img(m->mesh_agg_img, D);
-    o = MlpOut(); o.residual = m->mesh_lat; o.out = m->mesh_lat; o.out_img = m->mesh_lat_img;
-    if ((rc = run_mlp(c, m->proc_n_mesh[k], m->num_mesh, 2, s, o))) return rc;
-  }
+  MlpOut o = latent_new(m, m->mesh_edge, m->mesh_edge_img);
+  return run_mlp(c, m->enc_e_mesh, m->e_mesh, 1, s, o);
+}
 
-  // ---------------- decoder: mesh2grid_gnn (graphcast.py:641-678) ------------------
+int stage_process_step(StepCtx& c, int k) {
+  const gcb_model* m = c.m;
+  GCB_CHECK_ARG(k >= 0 && k < m->msg_steps, "message-passing step out of range");
+  int rc;
+  gcb_segment s[3];
+  const int D = 512;
+  const bool last = (k == m->msg_steps - 1);
+  // m = LN.MLP([e | v[snd] | v[rcv]]) -> mesh_msg;  e += m (skipped on the last step: the
+  // updated edge latents are never read again).
+  MlpOut o;
+  if (!last) o = latent_update(m, m->mesh_edge, m->mesh_edge_img);
+  o.out_y = m->mesh_msg;
+  if ((rc = run_edge_mlp(c, m->proc_e_mesh[k], &m->proc_e_mesh_split[k], m->e_mesh, m->mesh_edge_img,
+                         m->mesh_lat, m->mesh_lat_img, m->num_mesh, m->mesh_snd, m->proj_mesh_a,
+                         m->mesh_lat, m->mesh_lat_img, mesh_rows(m), m->mesh_rcv, m->proj_mesh_b, o)))
+    return rc;
+  if ((rc = segment_sum_launch(m->mesh_msg, D, m->mesh_row_ptr, mesh_rows(m), nullptr, 0, m->mesh_agg,
+                               D, D, m->mesh_agg_img, m->e_mesh, c.stream))) return rc;
+  c.launches += 1;
+  // v += LN.MLP([v | agg])
+  s[0] = seg_img(m->mesh_lat_img, D);
+  s[1] = seg_img(m->mesh_agg_img, D);
+  o = latent_update(m, m->mesh_lat, m->mesh_lat_img);
+  return run_mlp(c, m->proc_n_mesh[k], mesh_rows(m), 2, s, o);
+}
+
+// ---------------- decoder: mesh2grid_gnn (graphcast.py:641-678) ------------------
+int stage_decode(StepCtx& c, float* grid_out) {
+  const gcb_model* m = c.m;
+  int rc;
+  gcb_segment s[3];
+  const int D = 512;
+  const int ng = grid_rows(m);
+  GCB_CHECK_ARG(m->e_m2g == 3 * ng, "mesh2grid must have fan-in 3 over the (owned) grid rows");
   s[0] = seg(m->m2g_feat, nullptr, 4, 16, 4);
-  o = MlpOut(); o.out_img = m->edge_a_img;
+  MlpOut o; o.out_img = m->edge_a_img;
   if ((rc = run_mlp(c, m->enc_e_m2g, m->e_m2g, 1, s, o))) return rc;
   // m3 = LN.MLP([e3 | v[snd] | vg1[rcv]]) -> edge_b
   o = MlpOut(); o.out = m->edge_b;
   if ((rc = run_edge_mlp(c, m->proc_e_m2g, &m->proc_e_m2g_split, m->e_m2g, m->edge_a_img,
                          m->mesh_lat, m->mesh_lat_img, m->num_mesh, m->m2g_snd, m->proj_mesh_a,
-                         m->grid_lat, m->grid_lat_img, m->num_grid, m->m2g_rcv, m->proj_grid, o)))
+                         m->grid_lat, m->grid_lat_img, ng, m->m2g_rcv, m->proj_grid, o)))
     return rc;
   // sum of the 3 incoming messages of every grid node, as an operand image
-  if ((rc = to_image(c, m->edge_b, D, 3, m->num_grid, D, m->grid_agg_img))) return rc;
+  if ((rc = to_image(c, m->edge_b, D, 3, ng, D, m->grid_agg_img))) return rc;
   // vg2 = vg1 + LN.MLP([vg1 | agg3])  (in place)
   s[0] = seg_img(m->grid_lat_img, D);
   s[1] = seg_img(m->grid_agg_img, D);
-  o = MlpOut(); o.residual = m->grid_lat; o.out = m->grid_lat; o.out_img = m->grid_lat_img;
-  if ((rc = run_mlp(c, m->proc_n_grid_m2g, m->num_grid, 2, s, o))) return rc;
+  o = latent_update(m, m->grid_lat, m->grid_lat_img);
+  if ((rc = run_mlp(c, m->proc_n_grid_m2g, ng, 2, s, o))) return rc;
   // out = MLP(vg2), no LayerNorm (deep_typed_graph_net.py:314-322)
   s[0] = seg_img(m->grid_lat_img, D);
   o = MlpOut(); o.out = grid_out; o.ld_out = 256;
-  if ((rc = run_mlp(c, m->dec_grid, m->num_grid, 1, s, o))) return rc;
+  return run_mlp(c, m->dec_grid, ng, 1, s, o);
+}
 
+int forward_eager(const gcb_model* m, const void* grid_in_img, float* grid_out, void* stream,
+                  int32_t* launches) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  StepCtx c{m, static_cast<cudaStream_t>(stream), 0};
+  if ((rc = stage_encode(c, grid_in_img))) return rc;
+  if ((rc = stage_process_embed(c))) return rc;
+  for (int k = 0; k < m->msg_steps; ++k)
+    if ((rc = stage_process_step(c, k))) return rc;
+  if ((rc = stage_decode(c, grid_out))) return rc;
   if (launches) *launches = c.launches;
   return GCB_OK;
 }
 
 }  // namespace
+
+int gcb_forward_stage(const gcb_model* m, int32_t stage, int32_t step, const void* grid_in_img,
+                      float* grid_out, void* stream, int32_t* launches) {
+  GCB_CHECK_ARG(m != nullptr, "null model");
+  int rc = check_model(m);
+  if (rc) return rc;
+  StepCtx c{m, static_cast<cudaStream_t>(stream), 0};
+  switch (stage) {
+    case GCB_STAGE_ENCODE:
+      GCB_CHECK_ARG(grid_in_img != nullptr, "ENCODE needs grid_in_img");
+      rc = stage_encode(c, grid_in_img);
+      break;
+    case GCB_STAGE_PROCESS_EMBED: rc = stage_process_embed(c); break;
+    case GCB_STAGE_PROCESS_STEP: rc = stage_process_step(c, step); break;
+    case GCB_STAGE_DECODE:
+      GCB_CHECK_ARG(grid_out != nullptr, "DECODE needs grid_out");
+      rc = stage_decode(c, grid_out);
+      break;
+    default: return fail(GCB_ERR_INVALID, "invalid argument: unknown stage");
+  }
+  if (launches) *launches = c.launches;
+  return rc;
+}
 
 int gcb_set_cluster_size(int32_t ctas) {
   GCB_CHECK_ARG(ctas == 1 || ctas == 2 || ctas == 4, "cluster size must be 1, 2 or 4");

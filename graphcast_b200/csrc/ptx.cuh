@@ -86,6 +86,11 @@ __device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// Same for global memory: generic-proxy st.global made visible to later bulk copies
+// (cp.async.bulk reads through the async proxy) that are ordered after this thread.
+__device__ __forceinline__ void fence_proxy_async_global() {
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before_sync() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -164,6 +169,11 @@ __device__ __forceinline__ void st_cluster_f32x2(uint32_t raddr, float a, float 
 __device__ __forceinline__ void st_async_f32x2(uint32_t raddr, float a, float b, uint32_t rbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
                ::"r"(raddr), "f"(a), "f"(b), "r"(rbar) : "memory");
+}
+// Arrive with release at cluster scope on an mbarrier of THIS CTA (pairs with a
+// mbar_wait_cluster by a thread that then acts on behalf of the whole cluster).
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
 // Arrive (release at cluster scope) on an mbarrier of another CTA of the cluster.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t raddr) {
@@ -284,6 +294,17 @@ __device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t cta
       "[%0], %1;" ::"r"(smem_addr(bar)),
       "h"(cta_mask)
       : "memory");
+}
+
+// ---- warpgroup register re-allocation -----------------------------------------------
+// All four warps of a warpgroup (warps 4k..4k+3) must execute the same setmaxnreg.
+template <int kRegs>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+template <int kRegs>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
 }
 
 // ---- misc ---------------------------------------------------------------------

@@ -49,7 +49,8 @@ class Engine:
   def __init__(self, static_graph: graph_lib.StaticGraph,
                params: Mapping[str, Mapping[str, np.ndarray]], *,
                c_in: int, n_out: int, msg_steps: int, precision: str = "bf16x3",
-               device: Optional[torch.device] = None, pregather: bool = True):
+               device: Optional[torch.device] = None, pregather: bool = True,
+               fuse: bool = True, chain_lag: int = 0, image_residual: bool = False):
     if precision not in _native.PRECISIONS:
       raise ValueError(f"unknown precision {precision!r}; expected one of "
                        f"{sorted(_native.PRECISIONS)}")
@@ -70,6 +71,12 @@ class Engine:
     # pregather: evaluate the first edge-MLP layer as  e@W_e + (v@W_s)[snd] + (v@W_r)[rcv]
     # (node-level projections gathered in the epilogue) -- 30 % fewer tensor-core MACs.
     self.pregather = bool(pregather)
+    # fuse: both linears of every MLP run as one chain launch, the hidden activation stays in
+    # an L2-resident scratch (gcb_chain_forward); False = one launch per linear (round-1 path).
+    self.fuse = bool(fuse)
+    self.chain_lag = int(chain_lag)
+    # image_residual: latent streams live in HBM only as operand images (no fp32 masters).
+    self.image_residual = bool(image_residual)
     self.c_in_pad = _ceil(c_in + 3, 16)
     self.c_in_valid = _ceil(c_in + 3, 4)
     g = static_graph
@@ -265,6 +272,13 @@ class Engine:
                  "grid_lat_img", "mesh_lat", "mesh_lat_img", "mesh_agg", "mesh_agg_img",
                  "mesh_edge", "mesh_edge_img", "mesh_msg", "grid_agg_img"):
       setattr(m, name, self._ptr(getattr(self, name)))
+    m.fuse, m.chain_lag = (1 if self.fuse else 0), self.chain_lag
+    m.image_residual = 1 if self.image_residual else 0
+    nbytes = self._lib.gcb_chain_scratch_bytes(self.device.index or 0, 2, 2, 2)
+    if nbytes <= 0:
+      raise RuntimeError("gcb_chain_scratch_bytes failed")
+    self.chain_scratch = torch.zeros([nbytes], dtype=torch.uint8, device=self.device)
+    m.chain_scratch = self._ptr(self.chain_scratch)
     if self.pregather:
       self.proj_grid = f(m.num_grid, LATENT)
       self.proj_mesh_a, self.proj_mesh_b = f(m.num_mesh, LATENT), f(m.num_mesh, LATENT)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GCB_ABI_VERSION 1
+#define GCB_ABI_VERSION 2
 
 typedef enum {
   GCB_OK = 0,
@@ -192,6 +192,54 @@ int gcb_unpack_grid_outputs(const float* y, int32_t ld_y, int32_t n_out, int64_t
                             const float* add_planes, const int32_t* add_plane_index,
                             float* planes_out, void* stream);
 
+/* ---- fused layer chains ---------------------------------------------------------------
+ * A CHAIN runs up to GCB_MAX_CHAIN fused layers over the same `rows` rows in ONE kernel: a
+ * cluster pair owns a 128-row tile and takes it through layer 0, 1, ... while the intermediate
+ * results stay on chip -- each layer that later layers consume writes its result (as an
+ * operand image) into a small per-cluster SCRATCH ring that lives in the 126 MB L2 and is
+ * streamed back by TMA as the A operand of the consumer; it is overwritten in place tile after
+ * tile, so it never has to reach HBM.  This is how the two linears of every MLP of
+ * build_mlp_with_maybe_layer_norm (utils/legacy/deep_typed_graph_net.py:205-247) execute as one
+ * launch with the [rows, 512] hidden activation never written to HBM.
+ * All layers of a chain have n = n_valid = 512.  Layer results are bit-identical to running the
+ * same layers one by one through gcb_layer_forward. */
+#define GCB_MAX_CHAIN 4
+
+typedef struct {
+  int32_t nseg;             /* 1..3 */
+  gcb_segment seg[3];       /* as in gcb_layer_desc; ignored when seg_from[s] >= 0 (set k only) */
+  int32_t seg_from[3];      /* -1: external segment (table / img);  j >= 0: the result of layer j
+                             * (j < this layer, which must have keep = 1), k = 512 */
+  const void* w_packed; const float* bias;      /* bias may be NULL (= 0) */
+  const float* ln_scale; const float* ln_offset;
+  int32_t act;              /* gcb_activation; SWISH and LayerNorm are mutually exclusive here */
+  int32_t keep;             /* 1: later layers of the chain consume this layer's result */
+  const float* residual; int32_t ld_res;
+  /* Alternative: the residual given as an operand image (x = hi + lo, two bf16: 2^-17 relative)
+   * of the [rows, 512] stream -- typically the SAME buffer as out_img (updated in place) and as a
+   * segment of an earlier layer, so that a latent has ONE representation in HBM instead of an
+   * fp32 master plus an image.  Excludes `residual` and `out`; LayerNorm layers only. */
+  const void* residual_img;
+  float* out;   int32_t ld_out;      /* residual + y, fp32 (optional) */
+  float* out_y; int32_t ld_out_y;    /* y alone, fp32 (optional) */
+  void* out_img;                     /* residual + y as an operand image (optional) */
+  int32_t n_pre_add; gcb_pre_add pre_add[2];
+} gcb_chain_layer;
+
+typedef struct {
+  int32_t rows;
+  int32_t nlayers;          /* 1..GCB_MAX_CHAIN */
+  int32_t precision;        /* GCB_PREC_BF16X3 or GCB_PREC_BF16 */
+  int32_t lag;              /* tiles a layer runs ahead of the next one (1 or 2; 0 = default 1) */
+  void* scratch;            /* gcb_chain_scratch_bytes() bytes, 16-byte aligned */
+  gcb_chain_layer layer[GCB_MAX_CHAIN];
+} gcb_chain_desc;
+
+/* Scratch bytes a chain launch needs on `device` (depends on the resident cluster count). */
+int64_t gcb_chain_scratch_bytes(int32_t device, int32_t n_keep_layers, int32_t lag,
+                                int32_t max_distance);
+int gcb_chain_forward(const gcb_chain_desc* d, void* stream);
+
 /* Top-of-atmosphere incident solar radiation on a lat / lon grid, integrated over a period ending
  * at each timestamp (replaces solar_radiation.get_toa_incident_solar_radiation,
  * weathernext/utils/solar_radiation.py:443-521; the forcing GraphCast needs at every target time).
@@ -277,7 +325,44 @@ typedef struct {
   float* mesh_edge; void* mesh_edge_img;   /* [e_mesh, 512] latent mesh edges */
   float* mesh_msg;      /* [e_mesh, 512] */
   void* grid_agg_img;   /* image [num_grid, 512]: summed mesh2grid messages */
+
+  /* Fused execution: 1 = every MLP (both linears, activation, LayerNorm, residual) is ONE
+   * gcb_chain_forward launch and its hidden activation never reaches HBM (needs chain_scratch;
+   * tensor-core precisions only -- the FP32_SIMT validation arm always runs layer by layer).
+   * 0 = one launch per linear through `hidden` (the round-1 path, kept as the reference the
+   * fused path must reproduce bit for bit). */
+  int32_t fuse;
+  int32_t chain_lag;        /* gcb_chain_desc.lag for those launches (0 = default) */
+  /* Node-partitioned execution (one rank of BASELINE config 4): the local node tables hold
+   * [owned rows | halo rows]; node updates, aggregation and the decoder cover the owned rows
+   * only, gathers and sender projections all local rows.  0 = every row is owned. */
+  int32_t num_grid_owned;
+  int32_t num_mesh_owned;
+  void* chain_scratch;      /* gcb_chain_scratch_bytes(device, 2, lag, 2) bytes */
+  /* 1 (needs fuse, pregather and a tensor-core precision): the latent streams grid_lat, mesh_lat
+   * and mesh_edge live in HBM ONLY as operand images; the residual of every update is read back
+   * from the image (x = hi + lo, two bf16: 2^-17 relative per update, cf. the 2^-17 operand split
+   * of the BF16X3 products) and the fp32 masters are neither written nor read.  Halves the HBM
+   * bytes of every residual update.  0 = fp32 masters next to the images (round-1 layout). */
+  int32_t image_residual;
+  int32_t pad_;
 } gcb_model;
+
+/* Stage-wise execution of the same step: gcb_forward == ENCODE, PROCESS_EMBED, PROCESS_STEP for
+ * step = 0..msg_steps-1, DECODE, in this order on one stream.  Used by the stage-wise parity
+ * tests and by the node-partitioned processor, which exchanges halo rows of mesh_lat between
+ * PROCESS_STEP calls (reference analogue: the all_gather / psum_scatter pair around every
+ * sharded gather / segment sum, utils/gather_scatter_ops.py:278,423).
+ *   ENCODE         grid2mesh GNN (graphcast.py:550-604): reads grid_in_img; leaves grid_lat = vg1,
+ *                  mesh_lat = vm1 (fp32 + images)
+ *   PROCESS_EMBED  mesh edge embedding (deep_typed_graph_net.py:250-271 for the mesh GNN)
+ *   PROCESS_STEP   one InteractionNetwork step + residuals (deep_typed_graph_net.py:372-393)
+ *   DECODE         mesh2grid GNN + output MLP (graphcast.py:641-678): writes grid_out */
+typedef enum {
+  GCB_STAGE_ENCODE = 0, GCB_STAGE_PROCESS_EMBED = 1, GCB_STAGE_PROCESS_STEP = 2, GCB_STAGE_DECODE = 3
+} gcb_stage;
+int gcb_forward_stage(const gcb_model* m, int32_t stage, int32_t step, const void* grid_in_img,
+                      float* grid_out, void* stream, int32_t* launches);
 
 /* One 6 h step for one batch element:
  *   grid_in_img  operand image of [num_grid, c_in_pad]  (from gcb_pack_grid_image)
@@ -301,12 +386,14 @@ int gcb_set_graph_replay(int32_t enabled);
  * kernel launched through this ABI is bracketed by CUDA events on its stream.
  * gcb_profile_end synchronises them and returns, per launch (in launch order,
  * at most `capacity` entries; *count = total launches): its kind, duration in ms,
- * and its ALGORITHMIC flops / HBM bytes (layer: 2*rows*K*n flops; inputs incl.
- * gathers + weights + outputs bytes.  segment sum reports only the output
- * bytes -- the caller adds edges*width*4).  Not thread safe. */
+ * and its ALGORITHMIC flops / HBM bytes (layer / chain: 2*rows*K*n flops per layer; inputs
+ * incl. gathers + weights + outputs bytes, results handed over inside a chain excluded.
+ * segment sum inside gcb_forward: message rows read + node rows written; through the public
+ * gcb_segment_sum* entry points only the output bytes -- the caller adds edges*width*4).
+ * Not thread safe. */
 typedef enum {
   GCB_KIND_LAYER_TC = 0, GCB_KIND_SEGMENT_SUM = 1, GCB_KIND_PACK = 2, GCB_KIND_UNPACK = 3,
-  GCB_KIND_LAYER_SIMT = 4, GCB_KIND_ROWS_TO_IMAGE = 5
+  GCB_KIND_LAYER_SIMT = 4, GCB_KIND_ROWS_TO_IMAGE = 5, GCB_KIND_CHAIN_TC = 6
 } gcb_kernel_kind;
 int gcb_profile_begin(void);
 int gcb_profile_end(int32_t capacity, int32_t* kinds, float* ms, double* flops, double* bytes,

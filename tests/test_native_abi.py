@@ -26,7 +26,7 @@ def test_every_declared_symbol_is_exported_and_bound():
   for name in names:
     assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert name in _native.EXPORTS, f"{name} has no ctypes signature in _native.EXPORTS"
-  assert lib.gcb_abi_version() == 1
+  assert lib.gcb_abi_version() == _native.GCB_ABI_VERSION == 2
 
 
 def test_missing_library_fails_loudly(monkeypatch):
@@ -78,3 +78,20 @@ def test_layer_validation_rejects_bad_descriptors():
   assert b"multiple of 16" in lib.gcb_last_error()
   with pytest.raises(ValueError):
     _native.check(-1, "x")
+
+
+def test_struct_layouts_match_the_header():
+  """ctypes mirrors vs the C structs: sizes computed by a C compiler from the header itself."""
+  import subprocess
+  import tempfile
+  src = ('#include <stdio.h>\n#include "graphcast_b200.h"\n'
+         'int main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(gcb_segment), sizeof(gcb_layer_desc),'
+         ' sizeof(gcb_chain_layer), sizeof(gcb_chain_desc), sizeof(gcb_model)); return 0;}\n')
+  with tempfile.TemporaryDirectory() as d:
+    c = os.path.join(d, "s.c")
+    open(c, "w").write(src)
+    exe = os.path.join(d, "s")
+    subprocess.run(["gcc", "-I", os.path.dirname(HEADER), c, "-o", exe], check=True)
+    sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+  assert sizes == [C.sizeof(_native.Segment), C.sizeof(_native.LayerDesc), C.sizeof(_native.ChainLayer),
+                   C.sizeof(_native.ChainDesc), C.sizeof(_native.Model)]
