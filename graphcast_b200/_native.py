@@ -81,11 +81,12 @@ class Model(C.Structure):
       ("fuse", C.c_int32), ("chain_lag", C.c_int32),
       ("num_grid_owned", C.c_int32), ("num_mesh_owned", C.c_int32),
       ("chain_scratch", _fp),
-      ("image_residual", C.c_int32), ("pad_", C.c_int32),
+      ("image_residual", C.c_int32), ("deep_chains", C.c_int32), ("proj_grid_b", _fp),
+      ("chain_scratch_bytes", C.c_int64),
   ]
 
 
-GCB_MAX_CHAIN = 4
+GCB_MAX_CHAIN = 6
 STAGE_ENCODE, STAGE_PROCESS_EMBED, STAGE_PROCESS_STEP, STAGE_DECODE = 0, 1, 2, 3
 
 
@@ -94,7 +95,7 @@ class ChainLayer(C.Structure):
               ("w_packed", _fp), ("bias", _fp), ("ln_scale", _fp), ("ln_offset", _fp),
               ("act", C.c_int32), ("keep", C.c_int32),
               ("residual", _fp), ("ld_res", C.c_int32),
-              ("residual_img", _fp),
+              ("residual_img", _fp), ("residual_keep", C.c_int32),
               ("out", _fp), ("ld_out", C.c_int32),
               ("out_y", _fp), ("ld_out_y", C.c_int32),
               ("out_img", _fp),
@@ -103,7 +104,8 @@ class ChainLayer(C.Structure):
 
 class ChainDesc(C.Structure):
   _fields_ = [("rows", C.c_int32), ("nlayers", C.c_int32), ("precision", C.c_int32),
-              ("lag", C.c_int32), ("scratch", _fp), ("layer", ChainLayer * GCB_MAX_CHAIN)]
+              ("lag", C.c_int32), ("order", C.c_int32), ("pad_", C.c_int32), ("scratch", _fp),
+              ("scratch_bytes", C.c_int64), ("layer", ChainLayer * GCB_MAX_CHAIN)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/graphcast_b200.h.

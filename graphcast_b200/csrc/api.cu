@@ -232,6 +232,7 @@ struct ChainShape {
   int maxdist = 1;     // largest (consumer layer - producer layer)
   int nslots = 2;
   bool pre = false;
+  bool big = false;    // more than 4 parameter vectors
 };
 
 int validate_chain(const gcb_chain_desc* d, ChainShape* shape) {
@@ -279,6 +280,13 @@ int validate_chain(const gcb_chain_desc* d, ChainShape* shape) {
     if (g.residual_img)
       GCB_CHECK_ARG(aligned16(g.residual_img) && !g.residual && !g.out,
                     "residual_img excludes residual and out");
+    if (g.residual_keep != 0) {
+      const int from = g.residual_keep - 1;
+      GCB_CHECK_ARG(from >= 0 && from < l && d->layer[from].keep && g.ln_scale != nullptr &&
+                        !g.residual && !g.residual_img && !g.out,
+                    "residual_keep must name an earlier kept layer (LayerNorm layers; excludes residual*/out)");
+      if (l - from > sh.maxdist) sh.maxdist = l - from;
+    }
     if (g.out) GCB_CHECK_ARG(aligned16(g.out) && g.ld_out % 4 == 0 && g.ld_out >= 512, "out unaligned");
     if (g.out_y) GCB_CHECK_ARG(aligned16(g.out_y) && g.ld_out_y % 4 == 0 && g.ld_out_y >= 512, "out_y unaligned");
     if (g.out_img) GCB_CHECK_ARG(aligned16(g.out_img), "out_img unaligned");
@@ -295,19 +303,27 @@ int validate_chain(const gcb_chain_desc* d, ChainShape* shape) {
     vecs += (g.bias ? 1 : 0) + (g.ln_scale ? 2 : 0);
     if (g.keep) ++sh.nq;
   }
-  GCB_CHECK_ARG(vecs <= gcb::kChainParamVecs, "too many bias / LayerNorm vectors for one chain");
+  GCB_CHECK_ARG(vecs <= 8, "too many bias / LayerNorm vectors for one chain (at most 8)");
+  sh.big = vecs > 4;
   const int lag = d->lag > 0 ? d->lag : 1;
-  sh.nslots = lag * sh.maxdist + 1;
+  GCB_CHECK_ARG(d->order == 0 || (d->order == 1 && d->nlayers >= 3),
+                "order must be 0, or 1 for chains of at least 3 layers");
+  sh.nslots = lag * sh.maxdist + (d->order == 0 ? 1 : 0);
   GCB_CHECK_ARG(sh.nslots <= gcb::kChainSlotsMax, "lag x distance too large");
-  if (sh.nq > 0) GCB_CHECK_ARG(d->scratch != nullptr && aligned16(d->scratch), "scratch null/unaligned");
+  if (sh.nq > 0) {
+    GCB_CHECK_ARG(d->scratch != nullptr && aligned16(d->scratch), "scratch null/unaligned");
+    const long long need = static_cast<long long>(sm_count_cached() / 2) * sh.nq * sh.nslots *
+                           gcb::kScratchTileBytes;
+    GCB_CHECK_ARG(d->scratch_bytes >= need, "scratch too small for this chain (kept layers x slots)");
+  }
   *shape = sh;
   return GCB_OK;
 }
 
-template <bool kSplit, bool kPre>
+template <bool kSplit, bool kPre, bool kBig>
 int launch_chain_variant(const gcb_chain_desc& d, const ChainShape& sh, cudaStream_t stream) {
-  using Cfg = gcb::ChainConfig<kSplit, kPre>;
-  auto kernel = gcb::mlp_chain_tc_kernel<kSplit, kPre>;
+  using Cfg = gcb::ChainConfig<kSplit, kPre, kBig>;
+  auto kernel = gcb::mlp_chain_tc_kernel<kSplit, kPre, kBig>;
   static bool attr_set[64] = {false};
   static int max_clusters[64] = {0};
   int dev = 0;
@@ -390,7 +406,7 @@ int run_mlp(StepCtx& c, const gcb_mlp& w, int rows, int nseg, const gcb_segment*
     gcb_chain_desc ch;
     memset(&ch, 0, sizeof(ch));
     ch.rows = rows; ch.nlayers = 2; ch.precision = c.m->precision; ch.lag = c.m->chain_lag;
-    ch.scratch = c.m->chain_scratch;
+    ch.scratch = c.m->chain_scratch; ch.scratch_bytes = c.m->chain_scratch_bytes;
     gcb_chain_layer& a = ch.layer[0];
     a.nseg = nseg;
     for (int s = 0; s < nseg; ++s) { a.seg[s] = segs[s]; a.seg_from[s] = -1; }
@@ -613,11 +629,17 @@ int gcb_chain_forward(const gcb_chain_desc* d, void* stream) {
     // (a residual_img that is also a segment of the chain is read from HBM once: not counted again)
   }
   ProfScope prof(st, GCB_KIND_CHAIN_TC, flops, bytes);
-  const bool split = d->precision == GCB_PREC_BF16X3;
-  if (split) return sh.pre ? launch_chain_variant<true, true>(*d, sh, st)
-                           : launch_chain_variant<true, false>(*d, sh, st);
-  return sh.pre ? launch_chain_variant<false, true>(*d, sh, st)
-                : launch_chain_variant<false, false>(*d, sh, st);
+  const int variant = (d->precision == GCB_PREC_BF16X3 ? 4 : 0) | (sh.pre ? 2 : 0) | (sh.big ? 1 : 0);
+  switch (variant) {
+    case 7: return launch_chain_variant<true, true, true>(*d, sh, st);
+    case 6: return launch_chain_variant<true, true, false>(*d, sh, st);
+    case 5: return launch_chain_variant<true, false, true>(*d, sh, st);
+    case 4: return launch_chain_variant<true, false, false>(*d, sh, st);
+    case 3: return launch_chain_variant<false, true, true>(*d, sh, st);
+    case 2: return launch_chain_variant<false, true, false>(*d, sh, st);
+    case 1: return launch_chain_variant<false, false, true>(*d, sh, st);
+    default: return launch_chain_variant<false, false, false>(*d, sh, st);
+  }
 }
 
 int gcb_segment_sum(const float* msg, int32_t ld_msg, const int32_t* row_ptr, int32_t num_nodes,
@@ -905,8 +927,222 @@ MlpOut latent_update(const gcb_model* m, float* master, void* img) {
 int grid_rows(const gcb_model* m) { return m->num_grid_owned > 0 ? m->num_grid_owned : m->num_grid; }
 int mesh_rows(const gcb_model* m) { return m->num_mesh_owned > 0 ? m->num_mesh_owned : m->num_mesh; }
 
+// ---- deep chains ("mega" mode) -----------------------------------------------------------
+// With image-only latents on one GPU the step is composed of chains of up to four layers, so
+// that whole blocks of the message-passing step are one launch and their intermediates stay
+// in the L2-resident scratch: [edge embedder MLP -> edge MLP] of the two bipartite graphs (the
+// embedded edge latents never exist in HBM), [node MLP -> sender / receiver projections of the
+// NEXT edge MLP], and the first processor step's [edge embedder -> edge MLP].
+bool mega(const gcb_model* m) {
+  return img_only(m) && m->deep_chains && m->num_grid_owned == 0 && m->num_mesh_owned == 0 &&
+         m->proj_grid_b != nullptr;
+}
+
+struct Chain {
+  gcb_chain_desc d;
+  Chain(const gcb_model* m, int rows, int order) {
+    memset(&d, 0, sizeof(d));
+    d.rows = rows; d.precision = m->precision; d.lag = m->chain_lag; d.order = order;
+    d.scratch = m->chain_scratch; d.scratch_bytes = m->chain_scratch_bytes;
+  }
+  gcb_chain_layer& add() {
+    gcb_chain_layer& l = d.layer[d.nlayers++];
+    l.seg_from[0] = l.seg_from[1] = l.seg_from[2] = -1;
+    return l;
+  }
+  int last() const { return d.nlayers - 1; }
+  // first linear of an MLP over external segments (swish, kept for the second linear)
+  gcb_chain_layer& mlp0(const gcb_mlp& w, int nseg, const gcb_segment* segs, const void* w0 = nullptr) {
+    gcb_chain_layer& l = add();
+    l.nseg = nseg;
+    for (int s = 0; s < nseg; ++s) l.seg[s] = segs[s];
+    l.w_packed = w0 ? w0 : w.w0_packed; l.bias = w.b0; l.act = GCB_ACT_SWISH; l.keep = 1;
+    return l;
+  }
+  // first linear of an MLP whose single input is the kept result of layer `from`
+  gcb_chain_layer& mlp0_from(const gcb_mlp& w, int from, const void* w0 = nullptr) {
+    gcb_chain_layer& l = add();
+    l.nseg = 1; l.seg_from[0] = from; l.seg[0].k = 512;
+    l.w_packed = w0 ? w0 : w.w0_packed; l.bias = w.b0; l.act = GCB_ACT_SWISH; l.keep = 1;
+    return l;
+  }
+  // second linear + LayerNorm of the MLP whose first linear is the previous layer
+  gcb_chain_layer& mlp1(const gcb_mlp& w) {
+    const int from = last();
+    gcb_chain_layer& l = add();
+    l.nseg = 1; l.seg_from[0] = from; l.seg[0].k = 512;
+    l.w_packed = w.w1_packed; l.bias = w.b1; l.ln_scale = w.ln_scale; l.ln_offset = w.ln_offset;
+    l.ld_res = l.ld_out = l.ld_out_y = 512;
+    return l;
+  }
+  // node-level projection of the kept result of layer `from` (no bias, no activation)
+  gcb_chain_layer& proj(int from, const void* w_packed, float* out) {
+    gcb_chain_layer& l = add();
+    l.nseg = 1; l.seg_from[0] = from; l.seg[0].k = 512;
+    l.w_packed = w_packed; l.out = out; l.ld_out = 512;
+    return l;
+  }
+  int run(StepCtx& c) {
+    const int rc = gcb_chain_forward(&d, c.stream);
+    if (rc == GCB_OK) c.launches += 1;
+    return rc;
+  }
+};
+
+void set_pre(gcb_chain_layer& l, const float* ps, const int32_t* snd, const float* pr, const int32_t* rcv) {
+  l.n_pre_add = 2;
+  l.pre_add[0].table = ps; l.pre_add[0].idx = snd; l.pre_add[0].ld = 512;
+  l.pre_add[1].table = pr; l.pre_add[1].idx = rcv; l.pre_add[1].ld = 512;
+}
+
+int mega_encode(StepCtx& c, const void* grid_in_img) {
+  const gcb_model* m = c.m;
+  int rc;
+  gcb_segment s[3];
+  const int D = 512;
+  {  // vg0 = LN.MLP(grid_in) -> grid_lat_img;  proj_grid = vg0 @ W_s(grid2mesh)
+    Chain ch(m, m->num_grid, 1);
+    s[0] = seg_img(grid_in_img, m->c_in_pad);
+    ch.mlp0(m->enc_grid, 1, s);
+    gcb_chain_layer& l1 = ch.mlp1(m->enc_grid);
+    l1.out_img = m->grid_lat_img; l1.keep = 1;
+    ch.proj(ch.last(), m->proc_e_g2m_split.ws_packed, m->proj_grid);
+    if ((rc = ch.run(c))) return rc;
+  }
+  {  // vm0 = LN.MLP(mesh_in) -> mesh_lat_img;  proj_mesh_a = vm0 @ W_r(grid2mesh)
+    Chain ch(m, m->num_mesh, 1);
+    s[0] = seg_img(m->mesh_in_img, m->c_in_pad);
+    ch.mlp0(m->enc_mesh, 1, s);
+    gcb_chain_layer& l1 = ch.mlp1(m->enc_mesh);
+    l1.out_img = m->mesh_lat_img; l1.keep = 1;
+    ch.proj(ch.last(), m->proc_e_g2m_split.wr_packed, m->proj_mesh_a);
+    if ((rc = ch.run(c))) return rc;
+  }
+  {  // e1 = LN.MLP(edge feats);  m1 = LN.MLP([e1 | vg0[snd] | vm0[rcv]]) -> edge_b
+    Chain ch(m, m->e_g2m, 1);
+    s[0] = seg(m->g2m_feat, nullptr, 4, 16, 4);
+    ch.mlp0(m->enc_e_g2m, 1, s);
+    ch.mlp1(m->enc_e_g2m).keep = 1;
+    set_pre(ch.mlp0_from(m->proc_e_g2m, ch.last(), m->proc_e_g2m_split.we_packed),
+            m->proj_grid, m->g2m_snd, m->proj_mesh_a, m->g2m_rcv);
+    ch.mlp1(m->proc_e_g2m).out = m->edge_b;
+    if ((rc = ch.run(c))) return rc;
+  }
+  if ((rc = segment_sum_launch(m->edge_b, D, m->g2m_row_ptr, m->num_mesh, m->g2m_heavy,
+                               m->n_g2m_heavy, m->mesh_agg, D, D, m->mesh_agg_img, m->e_g2m,
+                               c.stream))) return rc;
+  c.launches += 1;
+  {  // vm1 = vm0 + LN.MLP([vm0 | agg1]);  projections of the first processor step
+    Chain ch(m, m->num_mesh, 1);
+    s[0] = seg_img(m->mesh_lat_img, D);
+    s[1] = seg_img(m->mesh_agg_img, D);
+    ch.mlp0(m->proc_n_mesh_g2m, 2, s);
+    gcb_chain_layer& l1 = ch.mlp1(m->proc_n_mesh_g2m);
+    l1.residual_img = m->mesh_lat_img; l1.out_img = m->mesh_lat_img; l1.keep = 1;
+    const int v = ch.last();
+    ch.proj(v, m->proc_e_mesh_split[0].ws_packed, m->proj_mesh_a);
+    ch.proj(v, m->proc_e_mesh_split[0].wr_packed, m->proj_mesh_b);
+    if ((rc = ch.run(c))) return rc;
+  }
+  {  // vg1 = vg0 + LN.MLP([vg0]);  proj_grid_b = vg1 @ W_r(mesh2grid)
+    Chain ch(m, m->num_grid, 1);
+    s[0] = seg_img(m->grid_lat_img, D);
+    ch.mlp0(m->proc_n_grid_g2m, 1, s);
+    gcb_chain_layer& l1 = ch.mlp1(m->proc_n_grid_g2m);
+    l1.residual_img = m->grid_lat_img; l1.out_img = m->grid_lat_img; l1.keep = 1;
+    ch.proj(ch.last(), m->proc_e_m2g_split.wr_packed, m->proj_grid_b);
+    if ((rc = ch.run(c))) return rc;
+  }
+  return GCB_OK;
+}
+
+int mega_process_step(StepCtx& c, int k) {
+  const gcb_model* m = c.m;
+  GCB_CHECK_ARG(k >= 0 && k < m->msg_steps, "message-passing step out of range");
+  int rc;
+  gcb_segment s[3];
+  const int D = 512;
+  const bool last = (k == m->msg_steps - 1);
+  if (k == 0) {
+    // e0 = LN.MLP(edge feats);  m = LN.MLP([e0 | v[snd] | v[rcv]]);  e1 = e0 + m  (e0 stays on chip)
+    Chain ch(m, m->e_mesh, 1);
+    s[0] = seg(m->mesh_feat, nullptr, 4, 16, 4);
+    ch.mlp0(m->enc_e_mesh, 1, s);
+    ch.mlp1(m->enc_e_mesh).keep = 1;
+    const int e0 = ch.last();
+    set_pre(ch.mlp0_from(m->proc_e_mesh[0], e0, m->proc_e_mesh_split[0].we_packed),
+            m->proj_mesh_a, m->mesh_snd, m->proj_mesh_b, m->mesh_rcv);
+    gcb_chain_layer& l3 = ch.mlp1(m->proc_e_mesh[0]);
+    l3.out_y = m->mesh_msg;
+    if (!last) { l3.residual_keep = e0 + 1; l3.out_img = m->mesh_edge_img; }
+    if ((rc = ch.run(c))) return rc;
+  } else {
+    Chain ch(m, m->e_mesh, 0);
+    s[0] = seg_img(m->mesh_edge_img, D);
+    set_pre(ch.mlp0(m->proc_e_mesh[k], 1, s, m->proc_e_mesh_split[k].we_packed),
+            m->proj_mesh_a, m->mesh_snd, m->proj_mesh_b, m->mesh_rcv);
+    gcb_chain_layer& l1 = ch.mlp1(m->proc_e_mesh[k]);
+    l1.out_y = m->mesh_msg;
+    if (!last) { l1.residual_img = m->mesh_edge_img; l1.out_img = m->mesh_edge_img; }
+    if ((rc = ch.run(c))) return rc;
+  }
+  if ((rc = segment_sum_launch(m->mesh_msg, D, m->mesh_row_ptr, m->num_mesh, nullptr, 0, m->mesh_agg,
+                               D, D, m->mesh_agg_img, m->e_mesh, c.stream))) return rc;
+  c.launches += 1;
+  {  // v += LN.MLP([v | agg]);  projections of the next edge MLP (next step, or mesh2grid senders)
+    Chain ch(m, m->num_mesh, 1);
+    s[0] = seg_img(m->mesh_lat_img, D);
+    s[1] = seg_img(m->mesh_agg_img, D);
+    ch.mlp0(m->proc_n_mesh[k], 2, s);
+    gcb_chain_layer& l1 = ch.mlp1(m->proc_n_mesh[k]);
+    l1.residual_img = m->mesh_lat_img; l1.out_img = m->mesh_lat_img; l1.keep = 1;
+    const int v = ch.last();
+    if (!last) {
+      ch.proj(v, m->proc_e_mesh_split[k + 1].ws_packed, m->proj_mesh_a);
+      ch.proj(v, m->proc_e_mesh_split[k + 1].wr_packed, m->proj_mesh_b);
+    } else {
+      ch.proj(v, m->proc_e_m2g_split.ws_packed, m->proj_mesh_a);
+    }
+    if ((rc = ch.run(c))) return rc;
+  }
+  return GCB_OK;
+}
+
+int mega_decode(StepCtx& c, float* grid_out) {
+  const gcb_model* m = c.m;
+  int rc;
+  gcb_segment s[3];
+  const int D = 512;
+  GCB_CHECK_ARG(m->e_m2g == 3 * m->num_grid, "mesh2grid must have fan-in 3");
+  {  // e3 = LN.MLP(edge feats);  m3 = LN.MLP([e3 | v[snd] | vg1[rcv]]) -> edge_b
+    Chain ch(m, m->e_m2g, 1);
+    s[0] = seg(m->m2g_feat, nullptr, 4, 16, 4);
+    ch.mlp0(m->enc_e_m2g, 1, s);
+    ch.mlp1(m->enc_e_m2g).keep = 1;
+    set_pre(ch.mlp0_from(m->proc_e_m2g, ch.last(), m->proc_e_m2g_split.we_packed),
+            m->proj_mesh_a, m->m2g_snd, m->proj_grid_b, m->m2g_rcv);
+    ch.mlp1(m->proc_e_m2g).out = m->edge_b;
+    if ((rc = ch.run(c))) return rc;
+  }
+  if ((rc = to_image(c, m->edge_b, D, 3, m->num_grid, D, m->grid_agg_img))) return rc;
+  {  // vg2 = vg1 + LN.MLP([vg1 | agg3])
+    Chain ch(m, m->num_grid, 0);
+    s[0] = seg_img(m->grid_lat_img, D);
+    s[1] = seg_img(m->grid_agg_img, D);
+    ch.mlp0(m->proc_n_grid_m2g, 2, s);
+    gcb_chain_layer& l1 = ch.mlp1(m->proc_n_grid_m2g);
+    l1.residual_img = m->grid_lat_img; l1.out_img = m->grid_lat_img;
+    if ((rc = ch.run(c))) return rc;
+  }
+  // out = MLP(vg2), no LayerNorm (deep_typed_graph_net.py:314-322)
+  s[0] = seg_img(m->grid_lat_img, D);
+  MlpOut o; o.out = grid_out; o.ld_out = 256;
+  return run_mlp(c, m->dec_grid, m->num_grid, 1, s, o);
+}
+
 // ---------------- encoder: grid2mesh_gnn (graphcast.py:550-604) ----------------
 int stage_encode(StepCtx& c, const void* grid_in_img) {
+  if (mega(c.m)) return mega_encode(c, grid_in_img);
   const gcb_model* m = c.m;
   int rc;
   gcb_segment s[3];
@@ -949,6 +1185,7 @@ int stage_encode(StepCtx& c, const void* grid_in_img) {
 // ---------------- processor: mesh_gnn (graphcast.py:606-639) --------------------
 int stage_process_embed(StepCtx& c) {
   const gcb_model* m = c.m;
+  if (mega(m)) return GCB_OK;      // folded into the first step's edge chain
   gcb_segment s[3];
   s[0] = seg(m->mesh_feat, nullptr, 4, 16, 4);
   MlpOut o = latent_new(m, m->mesh_edge, m->mesh_edge_img);
@@ -957,6 +1194,7 @@ int stage_process_embed(StepCtx& c) {
 
 int stage_process_step(StepCtx& c, int k) {
   const gcb_model* m = c.m;
+  if (mega(m)) return mega_process_step(c, k);
   GCB_CHECK_ARG(k >= 0 && k < m->msg_steps, "message-passing step out of range");
   int rc;
   gcb_segment s[3];
@@ -984,6 +1222,7 @@ int stage_process_step(StepCtx& c, int k) {
 // ---------------- decoder: mesh2grid_gnn (graphcast.py:641-678) ------------------
 int stage_decode(StepCtx& c, float* grid_out) {
   const gcb_model* m = c.m;
+  if (mega(m)) return mega_decode(c, grid_out);
   int rc;
   gcb_segment s[3];
   const int D = 512;

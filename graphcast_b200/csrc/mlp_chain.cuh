@@ -17,7 +17,7 @@
 // step when the two linears were separate launches) on chip.
 //
 // Schedule.  Work is a sequence of UNITS (tile, layer); per cluster, step s runs the units
-// (tile_{s - l*lag}, layer l) for l = 0..L-1, i.e. a tile advances one layer per `lag` steps, so
+// (tile_{s - l*lag}, layer l) for l = 0..L-1 (or L-1..0: gcb_chain_desc.order), i.e. a tile advances one layer per `lag` steps, so
 // that between a layer's MMAs and the dependent layer's MMAs the tensor pipe has `lag` other
 // units to execute while the epilogue converts the accumulator and hands it over.  TMEM holds
 // two 128x256 fp32 accumulators (unit u uses buffer u & 1).
@@ -40,15 +40,17 @@ namespace gcb {
 
 constexpr int kChainSlotsMax = 5;
 constexpr int kScratchTileBytes = (kMaxN / kKStep) * GCB_A_IMAGE_BLOCK;   // 32 x 8448 = 270336
-constexpr int kChainParamVecs = 4;                // [512]-float vectors: biases, LN scale / offset
-constexpr int kChainTailBytes = 2560;
+constexpr int kChainTailBytes = 3072;
 
-template <bool kSplit, bool kPre>
+// kBig: room for 8 instead of 4 [512]-float parameter vectors (biases, LayerNorm scale / offset):
+// chains of two MLPs; costs 8 KB of shared memory (one operand stage in some variants).
+template <bool kSplit, bool kPre, bool kBig>
 struct ChainConfig {
+  static constexpr int kParamVecs = kBig ? 8 : 4;
   static constexpr int kAStageBytes = kSplit ? 2 * kAPartBytes : kAPartBytes;
   static constexpr int kBStageBytes = kSplit ? 2 * kBPartBytes : kBPartBytes;
   static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
-  static constexpr int kParamBytes = kChainParamVecs * kMaxN * 4;
+  static constexpr int kParamBytes = kParamVecs * kMaxN * 4;
   static constexpr int kGRegionBytes = kPre ? kGBytes : 0;
   static constexpr int kFixedBytes =
       kParamBytes + kEpiStageBytes + kGRegionBytes + kLnxBytes + kChainTailBytes;
@@ -82,13 +84,13 @@ struct ChainLayer {
   int bias_off, scale_off, offset_off;   // float offsets into the parameter area, -1 = none
   int keep_q;                            // scratch ring this layer writes, -1 = none
   int has_table;                         // some segment is an fp32 table (producer warps)
-  int pad_;
+  int res_q;                             // residual = the kept result in scratch ring res_q, -1 = none
 };
 
-template <bool kSplit, bool kPre>
+template <bool kSplit, bool kPre, bool kBig>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, const int nslots) {
-  using Cfg = ChainConfig<kSplit, kPre>;
+  using Cfg = ChainConfig<kSplit, kPre, kBig>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* stage_base = smem;
   float* s_param = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -117,6 +119,12 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
   const int lane = threadIdx.x & 31;
   const int L = d.nlayers;
   const int lag = d.lag > 0 ? d.lag : 1;
+  // Unit order inside a step: ascending (layer 0 first) or descending.  Descending, a kept
+  // result is consumed (by the next layer, one step later) BEFORE the producing layer's next
+  // unit writes again, so lag*distance slots per scratch ring suffice instead of lag*distance+1
+  // - what keeps the rings of a 4-layer chain inside the L2.  It shortens the distance between
+  // dependent units from L+1 to L-1 units, so it is used for chains of 3 and more layers.
+  const bool desc = d.order != 0;
   const long long rows_total = d.rows;
   const int num_tiles = (d.rows + kTileM - 1) / kTileM;
   const uint32_t crank = ptx::cluster_ctarank();
@@ -173,8 +181,11 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
       cl.res_img = static_cast<const uint8_t*>(gl.residual_img);
       cl.ld_res = gl.ld_res; cl.ld_out = gl.ld_out; cl.ld_outy = gl.ld_out_y;
       cl.nseg = gl.nseg; cl.n_pre = gl.n_pre_add;
+      cl.res_q = gl.residual_keep > 0 ? q_of_layer[gl.residual_keep - 1] : -1;
       cl.kind = gl.ln_scale != nullptr
-                    ? (gl.residual != nullptr ? kKindLNRes : (gl.residual_img != nullptr ? kKindLNImg : kKindLN))
+                    ? (gl.residual != nullptr
+                           ? kKindLNRes
+                           : ((gl.residual_img != nullptr || gl.residual_keep > 0) ? kKindLNImg : kKindLN))
                     : (gl.act == GCB_ACT_SWISH ? kKindSwish : kKindPlain);
       cl.bias_off = -1; cl.scale_off = -1; cl.offset_off = -1;
       if (gl.bias != nullptr) { cl.bias_off = off; off += kMaxN; }
@@ -248,7 +259,8 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
     const uint32_t a_half = a_bytes / 2;
     uint32_t stage = 0, phase = 0, tu = 0;
     for (int st = 0; st < nsteps; ++st) {
-      for (int l = 0; l < L; ++l) {
+      for (int li = 0; li < L; ++li) {
+        const int l = desc ? L - 1 - li : li;
         const int ti = st - l * lag;
         if (ti < 0 || ti >= T) continue;
         const uint32_t tile = cid + static_cast<uint32_t>(ti) * ncl;
@@ -302,7 +314,8 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
     const uint32_t idesc = ptx::make_idesc_bf16(kTileM, kUnitN);
     uint32_t stage = 0, phase = 0, u = 0;
     for (int st = 0; st < nsteps; ++st) {
-      for (int l = 0; l < L; ++l) {
+      for (int li = 0; li < L; ++li) {
+        const int l = desc ? L - 1 - li : li;
         const int ti = st - l * lag;
         if (ti < 0 || ti >= T) continue;
         const uint32_t buf = u & 1;
@@ -626,7 +639,8 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
     };
 
     for (int st = 0; st < nsteps; ++st) {
-      for (int l = 0; l < L; ++l) {
+      for (int li = 0; li < L; ++li) {
+        const int l = desc ? L - 1 - li : li;
         const int ti = st - l * lag;
         if (ti < 0 || ti >= T) continue;
         const uint32_t tile = cid + static_cast<uint32_t>(ti) * ncl;
@@ -647,6 +661,10 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
         cx.res_img = cl.res_img != nullptr
                          ? cl.res_img + static_cast<size_t>(tile) * (kMaxN / kKStep) * GCB_A_IMAGE_BLOCK
                          : nullptr;
+        // Residual = the kept result of an earlier layer: the slot this CTA's epilogue wrote for
+        // this tile (same threads, same rows and columns: program order makes it visible, and the
+        // slot cannot be rewritten before these warps reach tile ti + nslots themselves).
+        if (cl.res_q >= 0) cx.res_img = scratch_slot(cl.res_q, ti);
         if (ti + 1 < T && (cl.residual != nullptr || cl.res_img != nullptr)) {
           // Pull the residual of this layer's NEXT tile into L2 now (a whole step ahead).
           const uint32_t ntile = tile + ncl;
@@ -743,7 +761,8 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
       uint32_t gc = 0;
       const int gcol_lo = static_cast<int>(crank) * kUnitN, gcol_hi = gcol_lo + kUnitN;
       for (int st = 0; st < nsteps; ++st) {
-        for (int l = 0; l < L; ++l) {
+        for (int li = 0; li < L; ++li) {
+          const int l = desc ? L - 1 - li : li;
           const int ti = st - l * lag;
           if (ti < 0 || ti >= T) continue;
           const int n_pre = s_layer[l].n_pre;
@@ -794,7 +813,8 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
     } else if (do_a) {
       uint32_t it = 0;                               // global K-step counter (ring position)
       for (int st = 0; st < nsteps; ++st) {
-        for (int l = 0; l < L; ++l) {
+        for (int li = 0; li < L; ++li) {
+          const int l = desc ? L - 1 - li : li;
           const int ti = st - l * lag;
           if (ti < 0 || ti >= T) continue;
           const uint32_t tile = cid + static_cast<uint32_t>(ti) * ncl;

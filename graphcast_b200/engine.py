@@ -50,7 +50,8 @@ class Engine:
                params: Mapping[str, Mapping[str, np.ndarray]], *,
                c_in: int, n_out: int, msg_steps: int, precision: str = "bf16x3",
                device: Optional[torch.device] = None, pregather: bool = True,
-               fuse: bool = True, chain_lag: int = 0, image_residual: bool = False):
+               fuse: bool = True, chain_lag: int = 0, image_residual: bool = False,
+               deep_chains: bool = True):
     if precision not in _native.PRECISIONS:
       raise ValueError(f"unknown precision {precision!r}; expected one of "
                        f"{sorted(_native.PRECISIONS)}")
@@ -77,6 +78,9 @@ class Engine:
     self.chain_lag = int(chain_lag)
     # image_residual: latent streams live in HBM only as operand images (no fp32 masters).
     self.image_residual = bool(image_residual)
+    # deep_chains (with image_residual): [edge embedder -> edge MLP] and [node MLP -> next
+    # projections] as single launches; see gcb_model.deep_chains.
+    self.deep_chains = bool(deep_chains)
     self.c_in_pad = _ceil(c_in + 3, 16)
     self.c_in_valid = _ceil(c_in + 3, 4)
     g = static_graph
@@ -274,16 +278,19 @@ class Engine:
       setattr(m, name, self._ptr(getattr(self, name)))
     m.fuse, m.chain_lag = (1 if self.fuse else 0), self.chain_lag
     m.image_residual = 1 if self.image_residual else 0
-    nbytes = self._lib.gcb_chain_scratch_bytes(self.device.index or 0, 2, 2, 2)
+    m.deep_chains = 1 if self.deep_chains else 0
+    nbytes = self._lib.gcb_chain_scratch_bytes(self.device.index or 0, 3, 2, 2)
     if nbytes <= 0:
       raise RuntimeError("gcb_chain_scratch_bytes failed")
     self.chain_scratch = torch.zeros([nbytes], dtype=torch.uint8, device=self.device)
-    m.chain_scratch = self._ptr(self.chain_scratch)
+    m.chain_scratch, m.chain_scratch_bytes = self._ptr(self.chain_scratch), nbytes
     if self.pregather:
       self.proj_grid = f(m.num_grid, LATENT)
       self.proj_mesh_a, self.proj_mesh_b = f(m.num_mesh, LATENT), f(m.num_mesh, LATENT)
       m.proj_grid = self._ptr(self.proj_grid)
       m.proj_mesh_a, m.proj_mesh_b = self._ptr(self.proj_mesh_a), self._ptr(self.proj_mesh_b)
+      self.proj_grid_b = f(m.num_grid, LATENT)
+      m.proj_grid_b = self._ptr(self.proj_grid_b)
 
   def workspace_bytes(self) -> int:
     ts = [self.hidden, self.edge_a_img, self.edge_b, self.grid_in_img,
@@ -347,6 +354,24 @@ class Engine:
       cur.wait_stream(self._step_stream)
     self.launches_per_step = int(n.value)
     return grid_out
+
+  def run_stage(self, stage: str, step: int = 0, grid_in: Optional[torch.Tensor] = None,
+                grid_out: Optional[torch.Tensor] = None) -> int:
+    """One stage of the step on the current stream (gcb_forward_stage): "encode",
+    "process_embed", "process_step" (with `step`), "decode".  encode, process_embed,
+    process_step 0..msg_steps-1, decode == step().  Returns the number of kernel launches."""
+    stages = {"encode": _native.STAGE_ENCODE, "process_embed": _native.STAGE_PROCESS_EMBED,
+              "process_step": _native.STAGE_PROCESS_STEP, "decode": _native.STAGE_DECODE}
+    if stage not in stages:
+      raise ValueError(f"unknown stage {stage!r}")
+    grid_in = self.grid_in_img if grid_in is None else grid_in
+    grid_out = self.grid_out if grid_out is None else grid_out
+    n = C.c_int32(0)
+    with self._on_device():
+      _native.check(self._lib.gcb_forward_stage(
+          C.byref(self._model), stages[stage], step, grid_in.data_ptr(), grid_out.data_ptr(),
+          self._stream(), C.byref(n)), "gcb_forward_stage")
+    return int(n.value)
 
   def unpack_outputs(self, planes_out: torch.Tensor, grid_out: Optional[torch.Tensor] = None,
                      scale: Optional[torch.Tensor] = None, offset: Optional[torch.Tensor] = None,

@@ -203,7 +203,7 @@ int gcb_unpack_grid_outputs(const float* y, int32_t ld_y, int32_t n_out, int64_t
  * launch with the [rows, 512] hidden activation never written to HBM.
  * All layers of a chain have n = n_valid = 512.  Layer results are bit-identical to running the
  * same layers one by one through gcb_layer_forward. */
-#define GCB_MAX_CHAIN 4
+#define GCB_MAX_CHAIN 6
 
 typedef struct {
   int32_t nseg;             /* 1..3 */
@@ -220,6 +220,9 @@ typedef struct {
    * segment of an earlier layer, so that a latent has ONE representation in HBM instead of an
    * fp32 master plus an image.  Excludes `residual` and `out`; LayerNorm layers only. */
   const void* residual_img;
+  /* Or the kept result of an earlier layer of this chain: 0 = none, j + 1 = layer j (keep = 1).
+   * Excludes residual / residual_img / out.  (vg1 = vg0 + MLP(vg0) with vg0 never leaving the chip.) */
+  int32_t residual_keep;
   float* out;   int32_t ld_out;      /* residual + y, fp32 (optional) */
   float* out_y; int32_t ld_out_y;    /* y alone, fp32 (optional) */
   void* out_img;                     /* residual + y as an operand image (optional) */
@@ -231,7 +234,11 @@ typedef struct {
   int32_t nlayers;          /* 1..GCB_MAX_CHAIN */
   int32_t precision;        /* GCB_PREC_BF16X3 or GCB_PREC_BF16 */
   int32_t lag;              /* tiles a layer runs ahead of the next one (1 or 2; 0 = default 1) */
+  int32_t order;            /* unit order inside a pipeline step: 0 = layer 0 first; 1 = last layer
+                             * first (one scratch slot less per ring; for chains of >= 3 layers) */
+  int32_t pad_;
   void* scratch;            /* gcb_chain_scratch_bytes() bytes, 16-byte aligned */
+  int64_t scratch_bytes;    /* size of `scratch` (checked against what this chain needs) */
   gcb_chain_layer layer[GCB_MAX_CHAIN];
 } gcb_chain_desc;
 
@@ -338,14 +345,19 @@ typedef struct {
    * only, gathers and sender projections all local rows.  0 = every row is owned. */
   int32_t num_grid_owned;
   int32_t num_mesh_owned;
-  void* chain_scratch;      /* gcb_chain_scratch_bytes(device, 2, lag, 2) bytes */
+  void* chain_scratch;      /* chain_scratch_bytes >= gcb_chain_scratch_bytes(device, 3, lag, 2) */
   /* 1 (needs fuse, pregather and a tensor-core precision): the latent streams grid_lat, mesh_lat
    * and mesh_edge live in HBM ONLY as operand images; the residual of every update is read back
    * from the image (x = hi + lo, two bf16: 2^-17 relative per update, cf. the 2^-17 operand split
    * of the BF16X3 products) and the fp32 masters are neither written nor read.  Halves the HBM
    * bytes of every residual update.  0 = fp32 masters next to the images (round-1 layout). */
   int32_t image_residual;
-  int32_t pad_;
+  /* 1 (with image_residual, one GPU): compose the step from chains of up to four layers --
+   * [edge embedder MLP -> edge MLP], [node MLP -> projections of the next edge MLP] -- so that the
+   * embedded edge latents and the inputs of the projections never reach HBM (needs proj_grid_b). */
+  int32_t deep_chains;
+  float* proj_grid_b;       /* [num_grid, 512]: receiver projection of the mesh2grid edge MLP */
+  int64_t chain_scratch_bytes;
 } gcb_model;
 
 /* Stage-wise execution of the same step: gcb_forward == ENCODE, PROCESS_EMBED, PROCESS_STEP for

@@ -85,6 +85,75 @@ class Oracle:
     out.index_add_(0, segment_ids, data)
     return out
 
+  # The three GNN calls of GraphCast.__call__ as separate stages (graphcast.py:309-323), so that
+  # the 0.25 degree parity tests can check the CUDA path stage by stage.
+  def _t(self, a):
+    return torch.as_tensor(np.asarray(a)).to(self.dtype)
+
+  @staticmethod
+  def _idx(a):
+    return torch.as_tensor(np.asarray(a)).to(torch.int64)
+
+  def encoder(self, graph: Mapping[str, np.ndarray], grid_features, inter: Optional[dict] = None):
+    """grid2mesh_gnn (graphcast.py:550-604): [Ng,B,C_in] -> (vm1 [Nm,B,D], vg1 [Ng,B,D])."""
+    X = self._t(grid_features)
+    n_grid, batch, _ = X.shape
+    bcast = lambda f: self._t(f)[:, None, :].expand(-1, batch, -1)   # _add_batch_second_axis :726-730
+    sg, sm = bcast(graph["grid_node_feats"]), bcast(graph["mesh_node_feats"])
+    n_mesh = sm.shape[0]
+    grid_in = torch.cat([X, sg], dim=-1)
+    mesh_in = torch.cat([torch.zeros((n_mesh,) + tuple(X.shape[1:]), dtype=self.dtype), sm],
+                        dim=-1)                                 # :573-583
+    g = "grid2mesh_gnn"
+    vg0 = self.mlp(mlp_name(g, "encoder_nodes_", "grid_nodes"), [grid_in])
+    vm0 = self.mlp(mlp_name(g, "encoder_nodes_", "mesh_nodes"), [mesh_in])
+    e1 = self.mlp(mlp_name(g, "encoder_edges_", "grid2mesh"), [bcast(graph["g2m_edge_feats"])])
+    s1, r1 = self._idx(graph["g2m_senders"]), self._idx(graph["g2m_receivers"])
+    m1 = self.mlp(mlp_name(g, "processor_edges_0_", "grid2mesh"), [e1, vg0[s1], vm0[r1]])
+    agg1 = self.segment_sum(m1, r1, n_mesh)        # f32_aggregation is a no-op in f32
+    vm1 = vm0 + self.mlp(mlp_name(g, "processor_nodes_0_", "mesh_nodes"), [vm0, agg1])
+    vg1 = vg0 + self.mlp(mlp_name(g, "processor_nodes_0_", "grid_nodes"), [vg0])
+    if inter is not None:
+      inter.update(vg0=vg0, vm0=vm0, e1=e1, m1=m1, agg1=agg1, vm1=vm1, vg1=vg1)
+    return vm1, vg1
+
+  def processor(self, graph: Mapping[str, np.ndarray], vm1, inter: Optional[dict] = None):
+    """mesh_gnn (graphcast.py:606-639): all message-passing steps on the multi-mesh."""
+    v = self._t(vm1)
+    batch = v.shape[1]
+    bcast = lambda f: self._t(f)[:, None, :].expand(-1, batch, -1)
+    n_mesh = v.shape[0]
+    g = "mesh_gnn"
+    e = self.mlp(mlp_name(g, "encoder_edges_", "mesh"), [bcast(graph["mesh_edge_feats"])])
+    s2, r2 = self._idx(graph["mesh_senders"]), self._idx(graph["mesh_receivers"])
+    k = 0
+    while mlp_name(g, f"processor_edges_{k}_", "mesh") + "_mlp/~/linear_0" in self.p:
+      m = self.mlp(mlp_name(g, f"processor_edges_{k}_", "mesh"), [e, v[s2], v[r2]])
+      agg = self.segment_sum(m, r2, n_mesh)
+      v_new = v + self.mlp(mlp_name(g, f"processor_nodes_{k}_", "mesh_nodes"), [v, agg])
+      e = e + m
+      v = v_new
+      k += 1
+    if inter is not None:
+      inter.update(v_mesh=v, e_mesh=e)
+    return v
+
+  def decoder(self, graph: Mapping[str, np.ndarray], v_mesh, vg1, inter: Optional[dict] = None):
+    """mesh2grid_gnn + output MLP (graphcast.py:641-678) -> [Ng,B,n_out]."""
+    v, vg1 = self._t(v_mesh), self._t(vg1)
+    n_grid, batch = vg1.shape[0], vg1.shape[1]
+    bcast = lambda f: self._t(f)[:, None, :].expand(-1, batch, -1)
+    g = "mesh2grid_gnn"
+    e3 = self.mlp(mlp_name(g, "encoder_edges_", "mesh2grid"), [bcast(graph["m2g_edge_feats"])])
+    s3, r3 = self._idx(graph["m2g_senders"]), self._idx(graph["m2g_receivers"])
+    m3 = self.mlp(mlp_name(g, "processor_edges_0_", "mesh2grid"), [e3, v[s3], vg1[r3]])
+    agg3 = self.segment_sum(m3, r3, n_grid)
+    vg2 = vg1 + self.mlp(mlp_name(g, "processor_nodes_0_", "grid_nodes"), [vg1, agg3])
+    out = self.mlp(mlp_name(g, "decoder_nodes_", "grid_nodes"), [vg2], use_layer_norm=False)
+    if inter is not None:
+      inter.update(vg2=vg2)
+    return out
+
   def forward(self, graph: Mapping[str, np.ndarray], grid_features: np.ndarray,
               return_intermediates: bool = False):
     """One step.  grid_features [Ng, B, C_in] (already normalised + packed).
@@ -95,57 +164,11 @@ class Oracle:
       m2g_senders/m2g_receivers [E3], m2g_edge_feats [E3,4].
     Returns [Ng, B, n_out].
     """
-    t = lambda a: torch.as_tensor(np.asarray(a)).to(self.dtype)
-    idx = lambda a: torch.as_tensor(np.asarray(a)).to(torch.int64)
-    X = t(grid_features)
-    n_grid, batch, _ = X.shape
-    bcast = lambda f: t(f)[:, None, :].expand(-1, batch, -1)   # _add_batch_second_axis :726-730
-    inter = {}
-
-    # ---- grid2mesh_gnn (graphcast.py:550-604) ----
-    sg, sm = bcast(graph["grid_node_feats"]), bcast(graph["mesh_node_feats"])
-    n_mesh = sm.shape[0]
-    grid_in = torch.cat([X, sg], dim=-1)
-    mesh_in = torch.cat([torch.zeros((n_mesh,) + tuple(X.shape[1:]), dtype=self.dtype), sm],
-                        dim=-1)                                 # :573-583
-    g = "grid2mesh_gnn"
-    vg0 = self.mlp(mlp_name(g, "encoder_nodes_", "grid_nodes"), [grid_in])
-    vm0 = self.mlp(mlp_name(g, "encoder_nodes_", "mesh_nodes"), [mesh_in])
-    e1 = self.mlp(mlp_name(g, "encoder_edges_", "grid2mesh"), [bcast(graph["g2m_edge_feats"])])
-    s1, r1 = idx(graph["g2m_senders"]), idx(graph["g2m_receivers"])
-    m1 = self.mlp(mlp_name(g, "processor_edges_0_", "grid2mesh"), [e1, vg0[s1], vm0[r1]])
-    agg1 = self.segment_sum(m1, r1, n_mesh)        # f32_aggregation is a no-op in f32
-    vm1 = vm0 + self.mlp(mlp_name(g, "processor_nodes_0_", "mesh_nodes"), [vm0, agg1])
-    vg1 = vg0 + self.mlp(mlp_name(g, "processor_nodes_0_", "grid_nodes"), [vg0])
+    inter = {} if return_intermediates else None
+    vm1, vg1 = self.encoder(graph, grid_features, inter)
+    v = self.processor(graph, vm1, inter)
+    out = self.decoder(graph, v, vg1, inter)
     if return_intermediates:
-      inter.update(vg0=vg0, vm0=vm0, e1=e1, m1=m1, agg1=agg1, vm1=vm1, vg1=vg1)
-
-    # ---- mesh_gnn (graphcast.py:606-639) ----
-    g = "mesh_gnn"
-    e = self.mlp(mlp_name(g, "encoder_edges_", "mesh"), [bcast(graph["mesh_edge_feats"])])
-    s2, r2 = idx(graph["mesh_senders"]), idx(graph["mesh_receivers"])
-    v = vm1
-    k = 0
-    while mlp_name(g, f"processor_edges_{k}_", "mesh") + "_mlp/~/linear_0" in self.p:
-      m = self.mlp(mlp_name(g, f"processor_edges_{k}_", "mesh"), [e, v[s2], v[r2]])
-      agg = self.segment_sum(m, r2, n_mesh)
-      v_new = v + self.mlp(mlp_name(g, f"processor_nodes_{k}_", "mesh_nodes"), [v, agg])
-      e = e + m
-      v = v_new
-      k += 1
-    if return_intermediates:
-      inter.update(v_mesh=v, e_mesh=e)
-
-    # ---- mesh2grid_gnn (graphcast.py:641-678) ----
-    g = "mesh2grid_gnn"
-    e3 = self.mlp(mlp_name(g, "encoder_edges_", "mesh2grid"), [bcast(graph["m2g_edge_feats"])])
-    s3, r3 = idx(graph["m2g_senders"]), idx(graph["m2g_receivers"])
-    m3 = self.mlp(mlp_name(g, "processor_edges_0_", "mesh2grid"), [e3, v[s3], vg1[r3]])
-    agg3 = self.segment_sum(m3, r3, n_grid)
-    vg2 = vg1 + self.mlp(mlp_name(g, "processor_nodes_0_", "grid_nodes"), [vg1, agg3])
-    out = self.mlp(mlp_name(g, "decoder_nodes_", "grid_nodes"), [vg2], use_layer_norm=False)
-    if return_intermediates:
-      inter.update(vg2=vg2)
       return out, inter
     return out
 

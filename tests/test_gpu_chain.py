@@ -191,7 +191,7 @@ def test_two_layer_mlp_chain_is_bit_identical_to_two_layer_launches(prec, tol, l
   scratch = _scratch(lib, 1, lag, 1)
   ch = _native.ChainDesc()
   ch.rows, ch.nlayers, ch.precision, ch.lag = rows, 2, _native.PRECISIONS[prec], lag
-  ch.scratch = scratch.data_ptr()
+  ch.scratch, ch.scratch_bytes = scratch.data_ptr(), scratch.numel()
   _fill_chain_layer(ch.layer[0], segs, [-1] * len(segs), l0, act=True, keep=True, pre=pre)
   _fill_chain_layer(ch.layer[1], [None], [0], l1, act=False, keep=False, residual=resd, out=o2,
                     out_y=y2, out_img=img2)
@@ -241,7 +241,7 @@ def test_four_layer_chain_with_skip_consumers(lag):
   scratch = _scratch(lib, 2, lag, 2)
   ch = _native.ChainDesc()
   ch.rows, ch.nlayers, ch.precision, ch.lag = rows, 4, _native.PRECISIONS[prec], lag
-  ch.scratch = scratch.data_ptr()
+  ch.scratch, ch.scratch_bytes = scratch.data_ptr(), scratch.numel()
   _fill_chain_layer(ch.layer[0], [_seg_img(v_img, 512), _seg_img(a_img, 512)], [-1, -1], l0, act=True, keep=True)
   _fill_chain_layer(ch.layer[1], [None], [0], l1, act=False, keep=True, residual=vd, out=vnew2, out_img=vimg2)
   _fill_chain_layer(ch.layer[2], [None], [1], ps, act=False, keep=False, out=s2)
@@ -318,7 +318,7 @@ def test_image_residual_update_matches_the_fp32_master_update():
     y = torch.full((rows, 512), float("nan"), device=DEV)
     ch = _native.ChainDesc()
     ch.rows, ch.nlayers, ch.precision, ch.lag = rows, 2, _native.PRECISIONS[prec], 1
-    ch.scratch = scratch.data_ptr()
+    ch.scratch, ch.scratch_bytes = scratch.data_ptr(), scratch.numel()
     _fill_chain_layer(ch.layer[0], [_seg_img(out_img, 512), _seg_img(a_img, 512)], [-1, -1], l0, act=True, keep=True)
     _fill_chain_layer(ch.layer[1], [None], [0], l1, act=False, keep=False,
                       residual=None if image_residual else xm, out_y=y, out_img=out_img)
@@ -349,3 +349,107 @@ def test_image_residual_step_stays_within_the_parity_gate(msg_steps):
   eb = float(np.abs(yb - ref).max() / np.abs(ref).max())
   print(f"vs fp64 oracle: fp32 masters {ea:.3e}, image-only latents {eb:.3e}")
   assert eb <= 1e-4
+
+
+@pytest.mark.parametrize("lag", [1, 2])
+def test_descending_order_chain_is_bit_identical(lag):
+  """Same 4-layer node block with the last layer first inside each pipeline step (one scratch
+  slot less per ring)."""
+  lib = _native.lib()
+  prec = "bf16x3"
+  g = torch.Generator().manual_seed(13)
+  rows = 128 * 300 + 5
+  f = lambda *shape: torch.randn(*shape, generator=g)
+  nan = lambda: torch.full((rows, 512), float("nan"), device=DEV)
+  v, a = f(rows, 512), f(rows, 512)
+  vd, ad = v.to(DEV), a.to(DEV)
+  v_img, a_img = _image(lib, vd, rows, 512), _image(lib, ad, rows, 512)
+  l0 = Layer(lib, 1024, 1024, g, ln=False)
+  l1 = Layer(lib, 512, 512, g, ln=True)
+  ps = Layer(lib, 512, 512, g, ln=False, bias=False)
+  pr = Layer(lib, 512, 512, g, ln=False, bias=False)
+  outs = []
+  for order in (0, 1):
+    vnew, vimg, s_, r_ = nan(), torch.zeros_like(v_img), nan(), nan()
+    scratch = _scratch(lib, 2, lag, 2)
+    ch = _native.ChainDesc()
+    ch.rows, ch.nlayers, ch.precision, ch.lag, ch.order = rows, 4, _native.PRECISIONS[prec], lag, order
+    ch.scratch, ch.scratch_bytes = scratch.data_ptr(), scratch.numel()
+    _fill_chain_layer(ch.layer[0], [_seg_img(v_img, 512), _seg_img(a_img, 512)], [-1, -1], l0, act=True, keep=True)
+    _fill_chain_layer(ch.layer[1], [None], [0], l1, act=False, keep=True, residual=vd, out=vnew, out_img=vimg)
+    _fill_chain_layer(ch.layer[2], [None], [1], ps, act=False, keep=False, out=s_)
+    _fill_chain_layer(ch.layer[3], [None], [1], pr, act=False, keep=False, out=r_)
+    _native.check(lib.gcb_chain_forward(C.byref(ch), _stream()), "chain")
+    torch.cuda.synchronize()
+    outs.append((vnew, vimg, s_, r_))
+  n_img = (rows // 128) * 32 * 8448
+  for x, y in zip(outs[0], outs[1]):
+    assert torch.equal(x[:n_img] if x.dtype == torch.uint8 else x, y[:n_img] if y.dtype == torch.uint8 else y)
+
+
+def test_embedder_plus_edge_mlp_chain_with_on_chip_residual():
+  """[edge embedder MLP -> edge MLP] as one 4-layer chain, the embedded latent e0 kept on chip and
+  used both as the edge MLP's input and as its residual (e1 = e0 + m): against the same four layers
+  run one by one with e0 written to HBM."""
+  lib = _native.lib()
+  prec = "bf16x3"
+  g = torch.Generator().manual_seed(17)
+  rows, n_nodes = 128 * 290 + 31, 7000
+  f = lambda *shape: torch.randn(*shape, generator=g)
+  nan = lambda: torch.full((rows, 512), float("nan"), device=DEV)
+  feat = f(rows, 4).to(DEV)
+  e0l0, e0l1 = Layer(lib, 4, 16, g, ln=False), Layer(lib, 512, 512, g, ln=True)
+  m0, m1 = Layer(lib, 512, 512, g, ln=False), Layer(lib, 512, 512, g, ln=True)
+  pa, pb = f(n_nodes, 512).to(DEV), f(n_nodes, 512).to(DEV)
+  ia = torch.randint(0, n_nodes, (rows,), generator=g, dtype=torch.int32).to(DEV)
+  ib = torch.randint(0, n_nodes, (rows,), generator=g, dtype=torch.int32).to(DEV)
+  pre = [(pa, ia), (pb, ib)]
+  nbytes = lib.gcb_a_image_bytes(rows, 512)
+  zimg = lambda: torch.zeros(nbytes, dtype=torch.uint8, device=DEV)
+  # layer by layer: e0 as fp32 master (the residual) + image
+  hidden, e0_img, e0, msg1, e1_img = zimg(), zimg(), nan(), nan(), zimg()
+  _layer_forward(lib, prec, rows, [_seg_table(feat, 4, 16)], e0l0, act=True, out_img=hidden)
+  _layer_forward(lib, prec, rows, [_seg_img(hidden, 512)], e0l1, act=False, out=e0, out_img=e0_img)
+  _layer_forward(lib, prec, rows, [_seg_img(e0_img, 512)], m0, act=True, out_img=hidden, pre=pre)
+  e1 = nan()
+  _layer_forward(lib, prec, rows, [_seg_img(hidden, 512)], m1, act=False, residual=e0, out=e1, out_y=msg1,
+                 out_img=e1_img)
+  # one chain
+  msg2, e2_img = nan(), zimg()
+  scratch = _scratch(lib, 3, 1, 2)
+  ch = _native.ChainDesc()
+  ch.rows, ch.nlayers, ch.precision, ch.lag, ch.order = rows, 4, _native.PRECISIONS[prec], 1, 1
+  ch.scratch, ch.scratch_bytes = scratch.data_ptr(), scratch.numel()
+  _fill_chain_layer(ch.layer[0], [_seg_table(feat, 4, 16)], [-1], e0l0, act=True, keep=True)
+  _fill_chain_layer(ch.layer[1], [None], [0], e0l1, act=False, keep=True)
+  _fill_chain_layer(ch.layer[2], [None], [1], m0, act=True, keep=True, pre=pre)
+  _fill_chain_layer(ch.layer[3], [None], [2], m1, act=False, keep=False, out_y=msg2, out_img=e2_img)
+  ch.layer[3].residual_keep = 2
+  _native.check(lib.gcb_chain_forward(C.byref(ch), _stream()), "chain")
+  torch.cuda.synchronize()
+  assert torch.equal(msg1, msg2)                    # the MLP outputs are bit-identical
+  # e1 = e0 + m: the chain adds the image form of e0 (hi + lo, 2^-17), the reference its fp32 master
+  x1, x2 = _decode_image(e1_img, rows), _decode_image(e2_img, rows)
+  assert float(np.abs(x1 - x2).max() / np.abs(x1).max()) < 2 ** -15
+
+
+@pytest.mark.parametrize("deep", [False, True])
+def test_image_residual_step_stagewise_and_deep_chains(deep):
+  g, params, x = _cases.small_case(c_in=31, n_out=23, msg_steps=3, batch=1)
+  ref = oracle_gnn.Oracle(params, torch.float64).forward(g.as_dict(), x).numpy()
+  eng = engine.Engine(g, params, c_in=31, n_out=23, msg_steps=3, precision="bf16x3",
+                      image_residual=True, deep_chains=deep)
+  y = eng.forward_features(torch.as_tensor(x)).cpu().numpy()
+  err = float(np.abs(y - ref).max() / np.abs(ref).max())
+  print(f"image-only latents, deep_chains={deep}: {err:.3e} vs fp64 oracle, {eng.launches_per_step} launches")
+  assert err <= 1e-4
+  # stage by stage == whole step
+  planes = torch.as_tensor(x[:, 0, :]).t().contiguous().to(eng.device)
+  eng.pack_inputs(planes)
+  n = eng.run_stage("encode") + eng.run_stage("process_embed")
+  for k in range(3):
+    n += eng.run_stage("process_step", k)
+  n += eng.run_stage("decode")
+  torch.cuda.synchronize()
+  assert n == eng.launches_per_step
+  np.testing.assert_array_equal(eng.grid_out[:, :23].cpu().numpy(), y[:, 0])
