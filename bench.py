@@ -8,15 +8,20 @@ A "step" is one 6 h forecast step of GraphCast 0.25 deg (721x1440, 37 levels,
 mesh 6, latent 512, 16 message steps) on synthetic N(0,1) inputs with
 Haiku-default random weights.  Prints ONE JSON line on rank 0.
 
-  value    : steps/s with inputs resident in HBM (pack -> step -> unpack), CUDA
-             events, max over ranks; N>1 = one independent forecast (ensemble
-             member) per GPU, no data-path collective ("weak" scaling).
+  value    : steps/s with inputs resident in HBM (pack -> step -> unpack), timed with CUDA
+             events around K un-instrumented steps (the path a user runs: CUDA-graph replay of
+             the step), max over ranks; N>1 = one independent forecast (ensemble member) per
+             GPU, no data-path collective ("weak" scaling).
   e2e      : steps/s through the public API (GraphCast.__call__) with pinned HOST
              inputs: per step H2D of inputs+forcings and D2H of the predictions.
-  roofline : the dominant kernel (the tcgen05 fused MLP layer) -- algorithmic
-             FLOPs of all its launches in a step / their summed CUDA-event time.
-  cpu_baseline : the fp32 CPU oracle (torch-CPU, all host threads) on a bounded
-             sample, scaled by the algorithmic FLOP ratio (stated in `sample`).
+  roofline : the dominant kernel family (the tcgen05 fused layer / chain kernels) --
+             algorithmic FLOPs of all its launches in a step / their summed CUDA-event time,
+             measured in a SEPARATE profiling pass of the same loop (events around every launch,
+             direct launches); `hbm` gives every kernel's achieved GB/s and fraction of the
+             measured copy bandwidth; `traffic` is read from the committed ncu launch list.
+  cpu_baseline / --impl reference : the fp32 CPU oracle (torch-CPU) on a bounded sample of the
+             SAME workload: a contiguous block of 1/16 of the rows of every stage of the real
+             0.25 degree graph (oracle/sampled_step.py), scaled by the row fraction.
 """
 
 import argparse
@@ -118,72 +123,64 @@ def dist_env():
   return rank, world, local
 
 
+def _cpu_sample(args, torch, steps, warmup, threads=None):
+  """The bounded CPU sample shared by `cpu_baseline` and `--impl reference`: the fp32 oracle on a
+  contiguous block of `--cpu-fraction` of the rows of every stage of the real workload graph
+  (oracle/sampled_step.py); returns (seconds per sample (median), threads, description)."""
+  from graphcast_b200 import graph as graph_lib, graphcast, synthetic
+  from oracle import gnn as oracle_gnn, sampled_step
+  cores = os.cpu_count() or 1
+  res, mesh, task_name = WORKLOADS[args.workload]
+  task = getattr(graphcast, task_name)
+  lat, lon = synthetic.grid_coords(res)
+  g = graph_lib.cached_static_graph(grid_lat=lat, grid_lon=lon, mesh_size=mesh,
+                                    radius_query_fraction_edge_length=0.6)
+  c_in = synthetic.num_input_channels(task)
+  n_out = graphcast.num_outputs(task)
+  params = oracle_gnn.init_params(c_in=c_in, n_out=n_out, msg_steps=16, seed=1)
+  samp = sampled_step.SampledStep(g.as_dict(), params, c_in, args.cpu_fraction)
+  # Thread count: torch's CPU ops regress badly with 128 threads on the GPU boxes' hosts, so
+  # calibrate on one sample each (the first doubles as the page-fault warm-up), keep the fastest.
+  best = None
+  for n in ([threads] if threads else thread_candidates(cores)):
+    torch.set_num_threads(n)
+    t = samp.time_one()
+    if best is None or t < best[0]:
+      best = (t, n)
+  torch.set_num_threads(best[1])
+  for _ in range(warmup):
+    samp.run()
+  ts = [samp.time_one() for _ in range(max(steps, 1))]
+  dt = float(np.median(ts))
+  desc = (f"fp32 oracle on the first {args.cpu_fraction:.4f} of the rows of every stage of "
+          f"{args.workload} (real graph indices, full-size gather tables): {dt:.2f} s per sample "
+          f"measured (median of {len(ts)}), x{1.0 / args.cpu_fraction:.0f} per step")
+  return dt, best[1], desc
+
+
 def run_reference(args):
-  """CPU arm: the fp32 oracle (restatement of the reference; its JAX stack cannot
-  be installed here) on the host cores, bounded sample scaled by FLOPs."""
+  """CPU arm: the fp32 oracle (restatement of the reference; its JAX stack cannot be installed
+  here) on the host cores; each "step" is one bounded sample of the same workload."""
   rank, world, _ = dist_env()
   if rank != 0:
     return
   import torch
-  from graphcast_b200 import graph as graph_lib, graphcast, synthetic
-  from oracle import gnn as oracle_gnn
-  cores = os.cpu_count() or 1
-  res, mesh, task_name = WORKLOADS[args.workload]
-  task = getattr(graphcast, task_name)
-  # Bounded sample: every step is one full oracle pass over a reduced-resolution instance of
-  # the same model, scaled by algorithmic FLOPs.  The whole --steps/--warmup run must end
-  # within a few minutes, so fall back to the smaller sample when the requested one would
-  # not fit REFERENCE_BUDGET_S (an oracle pass over the 2 degree sample takes 4.5 s with 32 threads on a GPU box's host, 30 s on an 8-core VM).
-  cpu_sample = args.cpu_sample
-  if cpu_sample == "sample_2deg_13lvl" and (args.steps + args.warmup + 2) * 8.0 > REFERENCE_BUDGET_S:
-    cpu_sample = "tiny_4deg_13lvl"
-  args.cpu_sample = cpu_sample
-  s_res, s_mesh, s_task_name = WORKLOADS[args.cpu_sample]
-  s_task = getattr(graphcast, s_task_name)
-  lat, lon = synthetic.grid_coords(s_res)
-  g = graph_lib.cached_static_graph(grid_lat=lat, grid_lon=lon, mesh_size=s_mesh,
-                                    radius_query_fraction_edge_length=0.6)
-  c_in = synthetic.num_input_channels(s_task)
-  n_out = graphcast.num_outputs(s_task)
-  params = oracle_gnn.init_params(c_in=c_in, n_out=n_out, msg_steps=16, seed=1)
-  x = np.random.default_rng(0).standard_normal((g.num_grid_nodes, 1, c_in)).astype(np.float32)
-  orc = oracle_gnn.Oracle(params, torch.float32)
-  gd = g.as_dict()
-  sample_flops = algorithmic_flops(g.num_grid_nodes, g.num_mesh_nodes, len(g.g2m_senders),
-                                   len(g.mesh_senders), len(g.m2g_senders), c_in, n_out, 16)
-  # full-workload FLOPs from the known sizes of the named config
-  full = full_workload_sizes(args.workload)
-  full_flops = algorithmic_flops(*full)
-  scale = full_flops / sample_flops
-  # Thread count: the oracle's torch ops regress badly with 128 threads on the GPU boxes' hosts
-  # (64 s per 2-degree pass against 4.5 s with 32), so calibrate on one pass each, keep the fastest.
-  best = None
-  for nthreads in thread_candidates(cores):
-    torch.set_num_threads(nthreads)
-    tc = time.perf_counter()
-    orc.forward(gd, x)
-    tc = time.perf_counter() - tc
-    if best is None or tc < best[0]:
-      best = (tc, nthreads)
-  cores = best[1]
-  torch.set_num_threads(cores)
-  for _ in range(args.warmup):
-    orc.forward(gd, x)
-  t0 = time.perf_counter()
-  for _ in range(args.steps):
-    orc.forward(gd, x)
-  dt = (time.perf_counter() - t0) / args.steps
-  ms = dt * scale * 1e3
-  value = 1e3 / ms
-  sample = (f"{args.cpu_sample}: full fp32 oracle step ({sample_flops/1e12:.2f} TFLOP, {dt:.2f} s "
-            f"measured) scaled x{scale:.2f} by algorithmic FLOPs to {args.workload}")
+  t_wall = time.perf_counter()
+  dt, cores, desc = _cpu_sample(args, torch, args.steps, args.warmup)
+  s_per_step = dt / args.cpu_fraction
+  value = 1.0 / s_per_step
   line = {
       "impl": "reference", "metric": "6h-step forecasts/sec", "value": value, "unit": "steps/s",
-      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-      "data": "synthetic", "config": {"workload": args.workload, "cpu_sample": args.cpu_sample},
+      "data": "synthetic",
+      "config": {"workload": args.workload, "sample_fraction": args.cpu_fraction,
+                 "measured_ms_per_sample": dt * 1e3,
+                 "note": "ms_per_step = measured_ms_per_sample / sample_fraction (each timed step is "
+                         "a bounded sample of the workload, as the contract allows)",
+                 "wall_s": time.perf_counter() - t_wall},
       "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port",
-                       "sample": sample},
+                       "sample": desc},
       "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
       "gpu_launches": 0,
   }
@@ -216,41 +213,33 @@ def thread_candidates(cores):
 
 
 def cpu_baseline_sample(args, torch):
-  """Bounded CPU sample on rank 0 (reported beside the GPU number)."""
-  from graphcast_b200 import graph as graph_lib, graphcast, synthetic
-  from oracle import gnn as oracle_gnn
-  cores = os.cpu_count() or 1
-  torch.set_num_threads(cores)
-  s_res, s_mesh, s_task_name = WORKLOADS[args.cpu_sample]
-  s_task = getattr(graphcast, s_task_name)
-  lat, lon = synthetic.grid_coords(s_res)
-  g = graph_lib.cached_static_graph(grid_lat=lat, grid_lon=lon, mesh_size=s_mesh,
-                                    radius_query_fraction_edge_length=0.6)
-  c_in = synthetic.num_input_channels(s_task)
-  n_out = graphcast.num_outputs(s_task)
-  params = oracle_gnn.init_params(c_in=c_in, n_out=n_out, msg_steps=16, seed=1)
-  x = np.random.default_rng(0).standard_normal((g.num_grid_nodes, 1, c_in)).astype(np.float32)
-  orc = oracle_gnn.Oracle(params, torch.float32)
-  gd = g.as_dict()
-  sample_flops = algorithmic_flops(g.num_grid_nodes, g.num_mesh_nodes, len(g.g2m_senders),
-                                   len(g.mesh_senders), len(g.m2g_senders), c_in, n_out, 16)
-  full_flops = algorithmic_flops(*full_workload_sizes(args.workload))
-  # One full pass per candidate thread count (the first doubles as the page-fault warm-up);
-  # report the fastest.  128 threads are not tried: 64 s per pass against 4.5 s with 32.
-  dt = None
-  for nthreads in thread_candidates(cores):
-    torch.set_num_threads(nthreads)
-    t0 = time.perf_counter()
-    orc.forward(gd, x)
-    t = time.perf_counter() - t0
-    if dt is None or t < dt:
-      dt, used = t, nthreads
-  cores = used
-  scale = full_flops / sample_flops
-  return {"value": 1.0 / (dt * scale), "unit": "steps/s", "cores": cores, "kind": "port",
-          "sample": (f"{args.cpu_sample}: full fp32 oracle step ({sample_flops/1e12:.2f} TFLOP, "
-                     f"{dt:.2f} s measured) scaled x{scale:.2f} by algorithmic FLOPs to "
-                     f"{args.workload}")}
+  """Bounded CPU sample on rank 0 (reported beside the GPU number): same sampler as the
+  reference arm, 3 samples."""
+  dt, cores, desc = _cpu_sample(args, torch, steps=3, warmup=0)
+  return {"value": args.cpu_fraction / dt, "unit": "steps/s", "cores": cores, "kind": "port",
+          "sample": desc}
+
+
+def ncu_traffic(workload, precision):
+  """DRAM bytes per step of the tensor-core kernels from the committed ncu launch list of this
+  build (profiles/r02_launches_ncu.csv: dram__bytes_read.sum + dram__bytes_write.sum per
+  launch).  None when no list for this configuration is committed."""
+  path = os.path.join(REPO, "profiles", "r02_launches_ncu.csv")
+  if workload != DEFAULT_WORKLOAD or precision != "bf16x3" or not os.path.exists(path):
+    return None, None
+  tc, total = 0.0, 0.0
+  try:
+    for line in open(path):
+      if line.startswith("#") or line.startswith("id,"):
+        continue
+      parts = line.rstrip("\n").rsplit(",", 3)
+      name, rd, wr = parts[0], float(parts[2]), float(parts[3])
+      total += rd + wr
+      if "mlp_chain_tc_kernel" in name or "mlp_layer_tc_kernel" in name:
+        tc += rd + wr
+  except Exception:
+    return None, None
+  return tc, f"ncu, profiles/r02_launches_ncu.csv (whole step {total / 1e9:.1f} GB)"
 
 
 def run_b200(args):
@@ -280,7 +269,7 @@ def run_b200(args):
   params = graphcast.init_params(cfg, task, c_in, seed=1)
   model = graphcast.GraphCast(cfg, task, params=params, precision=args.precision, device=dev,
                               pregather=args.pregather, fuse=args.fuse, chain_lag=args.chain_lag,
-                              image_residual=args.image_residual)
+                              image_residual=args.image_residual, deep_chains=args.deep_chains)
   # First call builds the static graph, uploads weights, allocates the workspace.
   pred = model(inputs, template, forcings)
   torch.cuda.synchronize()
@@ -308,8 +297,7 @@ def run_b200(args):
   if world > 1:
     dist.barrier()
   torch.cuda.synchronize()
-  cap = 256 * args.steps
-  lib.gcb_profile_begin()
+  # Headline: K un-instrumented steps (gcb_forward replays its CUDA graph, as for any caller).
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   ev0.record()
   for _ in range(args.steps):
@@ -319,12 +307,25 @@ def run_b200(args):
   if world > 1:
     dist.barrier()
   elapsed_ms = ev0.elapsed_time(ev1)
+  clocks = sampler.stop() if rank == 0 else None
+
+  # Profiling pass (separate from the headline): the same loop with a CUDA-event pair around
+  # every launch (direct launches instead of graph replay) -> per-kernel durations.
+  prof_steps = max(1, min(args.steps, args.profile_steps))
+  cap = 256 * prof_steps
+  lib.gcb_profile_begin()
+  pv0, pv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  pv0.record()
+  for _ in range(prof_steps):
+    one_step()
+  pv1.record()
+  torch.cuda.synchronize()
+  prof_ms_per_step = pv0.elapsed_time(pv1) / prof_steps
   kinds = (C.c_int32 * cap)(); ms = (C.c_float * cap)()
   flops = (C.c_double * cap)(); nbytes = (C.c_double * cap)(); cnt = C.c_int32(0)
   _native.check(lib.gcb_profile_end(cap, kinds, ms, flops, nbytes, C.byref(cnt)), "profile_end")
   n_launch = min(cnt.value, cap)
-  per_step_launches = cnt.value // args.steps
-  clocks = sampler.stop() if rank == 0 else None
+  per_step_launches = cnt.value // prof_steps
 
   t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
   if world > 1:
@@ -335,20 +336,24 @@ def run_b200(args):
   if args.dump_launches and rank == 0:
     with open(args.dump_launches, "w") as f:
       f.write("idx,kind,ms,gflop,gbyte\n")
-      lo = (args.steps - 1) * per_step_launches
+      lo = (prof_steps - 1) * per_step_launches
       for i in range(lo, min(lo + per_step_launches, n_launch)):
         f.write(f"{i - lo},{kinds[i]},{ms[i]:.4f},{flops[i] / 1e9:.2f},{nbytes[i] / 1e9:.4f}\n")
   # per-kind aggregation (this rank)
   kind_names = {0: "mlp_layer_tc", 1: "segment_sum", 2: "pack", 3: "unpack", 4: "mlp_layer_simt",
-                5: "rows_to_image", 6: "mlp_layer_tc"}   # 6 = fused chain launches of the same kernel family
+                5: "rows_to_image", 6: "mlp_chain_tc", 7: "gather_rows"}
   agg = {}
   for i in range(n_launch):
     a = agg.setdefault(kind_names[kinds[i]], [0.0, 0.0, 0.0, 0])
     a[0] += ms[i]; a[1] += flops[i]; a[2] += nbytes[i]; a[3] += 1
   m = eng._model
   alg_flops = algorithmic_flops(m.num_grid, m.num_mesh, m.e_g2m, m.e_mesh, m.e_m2g, c_in, n_out, 16)
-  tc = agg.get("mlp_layer_tc", agg.get("mlp_layer_simt", [1e-9, 0, 0, 0]))
-  tc_ms_per_step = tc[0] / args.steps
+  # the tensor-core kernel family: single fused layers + fused chains (same MMA / epilogue code)
+  tc = [0.0, 0.0, 0.0, 0]
+  for k in ("mlp_layer_tc", "mlp_chain_tc", "mlp_layer_simt"):
+    if k in agg:
+      tc = [x + y for x, y in zip(tc, agg[k])]
+  tc_ms_per_step = max(tc[0] / prof_steps, 1e-9)
   achieved_tflops = alg_flops / (tc_ms_per_step * 1e-3) / 1e12
   peaks = {}
   try:
@@ -356,34 +361,40 @@ def run_b200(args):
   except Exception:
     pass
   peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-  peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PF"
+  peak_hbm = peaks.get("hbm_gbs", 6500.0)
+  peak_src = ("measured (MEASURED_PEAKS.json: bf16_tflops_sustained, hbm_gbs)" if peaks
+              else "fallback 1.4 PFLOP/s, 6.5 TB/s (B200_PROFILING.md)")
   products = {"bf16x3": 3, "bf16": 1, "fp32_simt": 1}[args.precision]
-  # MACs the kernel really issues (the split edge layers execute fewer than the reference
+  # MACs the kernels really issue (the split edge layers execute fewer than the reference
   # dataflow the algorithmic figure is defined on), times the products per MAC.
-  executed_tflops = (tc[1] / args.steps) * products / (tc_ms_per_step * 1e-3) / 1e12
-  # DRAM bytes of this kernel's launches in one step, from the committed ncu pass over the same
-  # build and workload (dram__bytes_read.sum + dram__bytes_write.sum, `profiles/r01_launches_v11_ncu.csv`:
-  # 110.9 GB read + 110.3 GB written; the algorithmic figure is 254.8 GB, the L2 absorbs part of
-  # the gathers).  Only meaningful for the configuration it was captured on.
-  traffic, traffic_src = None, None
-  if args.workload == DEFAULT_WORKLOAD and args.precision == "bf16x3" and args.pregather:
-    traffic, traffic_src = 221.2e9, "ncu, profiles/r01_launches_v11_ncu.csv"
+  executed_tflops = (tc[1] / prof_steps) * products / (tc_ms_per_step * 1e-3) / 1e12
+  traffic, traffic_src = ncu_traffic(args.workload, args.precision)
   roofline = {
-      "kernel": "gcb::mlp_layer_tc_kernel", "bound": "tensor",
+      "kernel": "gcb::mlp_chain_tc_kernel + gcb::mlp_layer_tc_kernel (fused tcgen05 layers)",
+      "bound": "tensor",
       "achieved": achieved_tflops, "peak": peak_tf, "unit": "TFLOP/s",
-      "frac": achieved_tflops / peak_tf, "traffic": traffic, "traffic_unit": "bytes per step (all launches of this kernel)",
+      "frac": achieved_tflops / peak_tf, "traffic": traffic,
+      "traffic_unit": "DRAM bytes per step, all launches of this kernel family",
       "traffic_source": traffic_src, "peak_source": peak_src,
-      "launches_per_step": tc[3] // args.steps, "kernel_ms_per_step": tc_ms_per_step,
-      "kernel_share_of_step": tc_ms_per_step / (elapsed_ms / args.steps),
+      "launches_per_step": tc[3] // prof_steps, "kernel_ms_per_step": tc_ms_per_step,
+      "kernel_share_of_step": tc_ms_per_step / prof_ms_per_step,
+      "profile_pass": {"steps": prof_steps, "ms_per_step": prof_ms_per_step,
+                       "note": "event pair around every launch, direct launches; the headline "
+                               "ms_per_step is timed separately without instrumentation"},
       "algorithmic_tflop_per_step": alg_flops / 1e12,
       "tensor_products_per_mac": products,
-      "executed_tflop_per_step": tc[1] / args.steps * products / 1e12,
+      "executed_tflop_per_step": tc[1] / prof_steps * products / 1e12,
       "executed_tensor_tflops": executed_tflops,
       "tensor_pipe_frac": executed_tflops / peak_tf,
-      "other_kernels_ms_per_step": {k: v[0] / args.steps for k, v in agg.items() if k != "mlp_layer_tc"},
-      "hbm": {k: {"GB_per_step": v[2] / args.steps / 1e9,
-                  "GBps": (v[2] / 1e9) / (v[0] * 1e-3) if v[0] > 0 else None}
+      "algorithmic_hbm_GB_per_step": sum(v[2] for v in agg.values()) / prof_steps / 1e9,
+      "other_kernels_ms_per_step": {k: v[0] / prof_steps for k, v in agg.items()
+                                    if not k.startswith("mlp_")},
+      # every kernel against the HBM roofline: algorithmic bytes / CUDA-event time / measured copy bandwidth
+      "hbm": {k: {"GB_per_step": v[2] / prof_steps / 1e9, "ms_per_step": v[0] / prof_steps,
+                  "GBps": (v[2] / 1e9) / (v[0] * 1e-3) if v[0] > 0 else None,
+                  "hbm_frac": ((v[2] / 1e9) / (v[0] * 1e-3) / peak_hbm) if v[0] > 0 else None}
               for k, v in agg.items()},
+      "hbm_peak_GBps": peak_hbm,
   }
 
   # ---------------- end-to-end through the public API ---------------------------
@@ -438,7 +449,7 @@ def run_b200(args):
                    "levels": len(task.pressure_levels), "latent": 512, "msg_steps": 16,
                    "batch": 1, "precision": args.precision, "cluster": args.cluster or "default(2)",
                    "pregather": bool(args.pregather), "fuse": bool(args.fuse), "chain_lag": args.chain_lag,
-                   "image_residual": bool(args.image_residual),
+                   "image_residual": bool(args.image_residual), "deep_chains": bool(args.deep_chains),
                    "parallelism": "1 forecast per GPU (ensemble members), no collective",
                    "l2_policy": "working set per step (>20 GB) far exceeds the 126 MB L2; no flush needed",
                    "setup_s": setup_s},
@@ -455,23 +466,165 @@ def run_b200(args):
     dist.destroy_process_group()
 
 
+def run_partitioned(args):
+  """BASELINE config 4: ONE forecast per step, mesh-node partitioned over all ranks (strong
+  scaling): receiver-owned edges, one grouped NCCL all-to-all-v of halo rows per message-passing
+  step (graphcast_b200/partitioned.py)."""
+  import torch
+  import torch.distributed as dist
+  from graphcast_b200 import _native, engine, graph as graph_lib, graphcast, partitioned, synthetic
+
+  rank, world, local = dist_env()
+  torch.cuda.set_device(local)
+  dev = torch.device(f"cuda:{local}")
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+  res, mesh, task_name = WORKLOADS[args.workload]
+  task = getattr(graphcast, task_name)
+  cfg = graphcast.ModelConfig(resolution=res, mesh_size=mesh, latent_size=512, gnn_msg_steps=16,
+                              hidden_layers=1, radius_query_fraction_edge_length=0.6)
+  c_in = synthetic.num_input_channels(task)
+  n_out = graphcast.num_outputs(task)
+  lat, lon = synthetic.grid_coords(res)
+  g = graph_lib.cached_static_graph(grid_lat=lat, grid_lon=lon, mesh_size=mesh,
+                                    radius_query_fraction_edge_length=0.6)
+  params = graphcast.init_params(cfg, task, c_in, seed=1)
+  pe = partitioned.PartitionedEngine(g, params, c_in=c_in, n_out=n_out, msg_steps=16, rank=rank,
+                                     world=world, device=dev, precision=args.precision)
+  lg = pe.local
+  gen = torch.Generator(device=dev).manual_seed(0)          # same full field on every rank
+  planes_full = torch.randn(c_in, g.num_grid_nodes, device=dev, generator=gen)
+  planes_local = planes_full[:, torch.as_tensor(lg.local_grid_ids, device=dev)].contiguous()
+  if not args.check:
+    del planes_full
+  n_owned = int(lg.grid_owned.size)
+  planes_out = torch.empty([n_out, n_owned], dtype=torch.float32, device=dev)
+
+  def one_step(timed_halo=False):
+    pe.step(planes_local, timed_halo)
+    with pe.engine._on_device():
+      _native.check(pe._lib.gcb_unpack_grid_outputs(
+          pe.engine.grid_out.data_ptr(), 256, n_out, n_owned, None, None, None, None,
+          planes_out.data_ptr(), pe.engine._stream()), "gcb_unpack_grid_outputs")
+
+  for _ in range(max(args.warmup, 3)):
+    one_step()
+  torch.cuda.synchronize()
+  sampler = ClockSampler(local)
+  if rank == 0:
+    sampler.start()
+  if world > 1:
+    dist.barrier()
+  torch.cuda.synchronize()
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  ev0.record()
+  for _ in range(args.steps):
+    one_step()
+  ev1.record()
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  ms_per_step = float(t.item()) / args.steps
+  clocks = sampler.stop() if rank == 0 else None
+  # Cost of the halo exchanges: the same K steps with the exchanges skipped (results are then
+  # wrong, the kernels and their sizes are the same), max over ranks; the difference is what the
+  # 17 exchanges of a step cost in latency, including the waiting they introduce.
+  pe.skip_exchange = True
+  one_step()
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  ev0.record()
+  for _ in range(args.steps):
+    one_step()
+  ev1.record()
+  torch.cuda.synchronize()
+  h = torch.tensor([ev0.elapsed_time(ev1) / args.steps], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(h, op=dist.ReduceOp.MAX)
+  pe.skip_exchange = False
+  one_step()                                               # restore a valid state for --check
+  torch.cuda.synchronize()
+
+  check = None
+  if args.check:
+    # partitioned output (gathered) against the single-GPU step with the same kernels
+    n_max = torch.tensor([n_owned], device=dev)
+    if world > 1:
+      dist.all_reduce(n_max, op=dist.ReduceOp.MAX)
+    pad = torch.zeros([int(n_max.item()), 256], dtype=torch.float32, device=dev)
+    pad[:n_owned] = pe.engine.grid_out[:n_owned]
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    if world > 1:
+      dist.all_gather(parts, pad)
+    else:
+      parts = [pad]
+    owners = [partitioned.build_local_graph(g, world, r).grid_owned for r in range(world)] if rank == 0 else None
+    if rank == 0:
+      del pe
+      torch.cuda.empty_cache()
+      eng = engine.Engine(g, params, c_in=c_in, n_out=n_out, msg_steps=16, precision=args.precision,
+                          device=dev, image_residual=False, deep_chains=False)
+      eng.pack_inputs(planes_full)
+      eng.step()
+      torch.cuda.synchronize()
+      full = eng.grid_out[:, :n_out]
+      scale = float(full.abs().max())
+      err = 0.0
+      for r in range(world):
+        ids = torch.as_tensor(owners[r], device=dev)
+        err = max(err, float((parts[r][:ids.numel(), :n_out] - full[ids]).abs().max()) / scale)
+      check = {"max_abs_rel_err_vs_single_gpu": err, "bitwise_equal": err == 0.0}
+
+  if rank == 0:
+    st = partitioned.plan_statistics(g, world) if world > 1 else None
+    line = {
+        "metric": "6h-step forecasts/sec", "value": 1e3 / ms_per_step, "unit": "steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": args.workload, "mode": "partitioned",
+                   "parallelism": f"one forecast over {world} GPUs: mesh nodes by recursive coordinate "
+                                  "bisection, edges owned by their receiver, grid nodes by containing "
+                                  "triangle; 17 halo exchanges (NCCL all_to_all_v of fp32 rows) per step",
+                   "ms_per_step_without_halo_exchange": float(h.item()),
+                   "halo_exchange_ms_per_step": ms_per_step - float(h.item()),
+                   "halo_exchanges_per_step": 17 if world > 1 else 0,
+                   "partition": st},
+        "clocks": clocks, "check": check,
+        "gpu_launches_per_step": None,
+    }
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
 def main():
   # Exactly one JSON line may reach stdout: libraries (NCCL's version banner, warnings) are
   # diverted to stderr by pointing fd 1 at fd 2 for the duration of the run.
   real_stdout = os.dup(1)
   os.dup2(2, 1)
   sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
-  os.environ["NCCL_DEBUG"] = os.environ.get("GCB_NCCL_DEBUG", "WARN")
+  os.environ["NCCL_DEBUG"] = os.environ.get("GCB_NCCL_DEBUG", "INFO")   # communicator lines on stderr
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
   ap.add_argument("--steps", type=int, default=10)
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+  ap.add_argument("--mode", choices=["auto", "replicas", "partitioned"], default="auto",
+                  help="partitioned (default for N > 1): ONE forecast over all GPUs, mesh-node partition "
+                       "+ NCCL halo exchange per message-passing step (strong scaling); replicas: one "
+                       "independent forecast per GPU, no collective (weak scaling)")
+  ap.add_argument("--check", action="store_true",
+                  help="partitioned mode: compare the gathered output with the single-GPU step")
   ap.add_argument("--workload", choices=sorted(WORKLOADS), default=DEFAULT_WORKLOAD)
   ap.add_argument("--precision", choices=["bf16x3", "bf16", "fp32_simt"], default="bf16x3")
-  ap.add_argument("--cpu-sample", dest="cpu_sample", choices=sorted(WORKLOADS),
-                  default="sample_2deg_13lvl",
-                  help="bounded CPU sample (a few seconds per step), scaled by algorithmic FLOPs")
+  ap.add_argument("--cpu-fraction", dest="cpu_fraction", type=float, default=1.0 / 16,
+                  help="row fraction of every stage of the workload the CPU sample runs")
+  ap.add_argument("--profile-steps", dest="profile_steps", type=int, default=5)
   ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=10)
   ap.add_argument("--skip-cpu-baseline", action="store_true")
   ap.add_argument("--cluster", type=int, default=0, help="CTAs per cluster (0 = library default)")
@@ -479,13 +632,17 @@ def main():
   ap.add_argument("--no-fuse", dest="fuse", action="store_false",
                   help="one launch per linear layer (hidden activations through HBM)")
   ap.add_argument("--chain-lag", dest="chain_lag", type=int, default=0)
-  ap.add_argument("--image-residual", dest="image_residual", action="store_true",
-                  help="latent streams as operand images only (no fp32 masters)")
+  ap.add_argument("--masters", dest="image_residual", action="store_false",
+                  help="keep fp32 masters of the latent streams next to the operand images")
+  ap.add_argument("--no-deep", dest="deep_chains", action="store_false",
+                  help="two-layer chains only (no [embedder -> edge MLP] / [node MLP -> projections] launches)")
   ap.add_argument("--no-pregather", dest="pregather", action="store_false",
                   help="evaluate the first edge-MLP layer over the concatenated K=1536 input")
   args = ap.parse_args()
   if args.impl == "reference":
     run_reference(args)
+  elif args.mode == "partitioned" or (args.mode == "auto" and dist_env()[1] > 1):
+    run_partitioned(args)
   else:
     run_b200(args)
 

@@ -766,6 +766,22 @@ int gcb_toa_incident_solar_radiation(const float* table, int32_t n_times, int32_
   return GCB_OK;
 }
 
+int gcb_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, int64_t n, float* dst,
+                    int32_t ld_dst, int32_t width, void* stream) {
+  GCB_CHECK_ARG(n >= 0 && width > 0 && width % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0 &&
+                    ld_src >= width && ld_dst >= width, "bad width / ld");
+  if (n == 0) return GCB_OK;
+  GCB_CHECK_ARG(src && idx && dst && aligned16(src) && aligned16(dst), "null/unaligned pointer");
+  long long blocks = (n + 7) / 8;
+  const long long cap = static_cast<long long>(sm_count_cached()) * 8;
+  if (blocks > cap) blocks = cap;
+  ProfScope prof(static_cast<cudaStream_t>(stream), GCB_KIND_GATHER, 0.0, 8.0 * n * width);
+  gcb::gather_rows_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, ld_src, idx, n, dst, ld_dst, width);
+  GCB_CUDA(cudaGetLastError());
+  return GCB_OK;
+}
+
 int gcb_rows_to_image(const float* src, int32_t ld, int32_t fan, int64_t rows, int32_t k,
                       void* img, void* stream) {
   GCB_CHECK_ARG(src && img && aligned16(src) && aligned16(img), "null/unaligned pointer");

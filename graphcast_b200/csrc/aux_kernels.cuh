@@ -112,6 +112,22 @@ segment_sum_kernel(const float* __restrict__ msg, int ld_msg, const int* __restr
   }
 }
 
+// dst[i, 0:width] = src[idx[i], 0:width]  (width a multiple of 4 floats).  The send side of the
+// halo exchange of the node-partitioned processor: boundary rows of the latent table, gathered
+// into one contiguous buffer per step.  One warp per row, float4 lanes: coalesced both ways.
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ src, int ld_src, const int* __restrict__ idx,
+                   long long n, float* __restrict__ dst, int ld_dst, int width) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  for (long long i = warp; i < n; i += nwarps) {
+    const float4* s = reinterpret_cast<const float4*>(src + static_cast<long long>(idx[i]) * ld_src);
+    float4* d = reinterpret_cast<float4*>(dst + i * ld_dst);
+    for (int c = lane; c < (width >> 2); c += 32) d[c] = __ldg(s + c);
+  }
+}
+
 // planes [n_ch, n_nodes] (+ node_static [n_nodes, n_static]) -> feats [n_nodes, ld],
 // feats[i, c] = (planes[c, i] - mean[c]) / scale[c]; 32x32 smem-tiled transpose so
 // both the plane reads (along nodes) and the feature writes (along channels) are

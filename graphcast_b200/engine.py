@@ -50,8 +50,8 @@ class Engine:
                params: Mapping[str, Mapping[str, np.ndarray]], *,
                c_in: int, n_out: int, msg_steps: int, precision: str = "bf16x3",
                device: Optional[torch.device] = None, pregather: bool = True,
-               fuse: bool = True, chain_lag: int = 0, image_residual: bool = False,
-               deep_chains: bool = True):
+               fuse: bool = True, chain_lag: int = 0, image_residual: bool = True,
+               deep_chains: bool = True, num_grid_owned: int = 0, num_mesh_owned: int = 0):
     if precision not in _native.PRECISIONS:
       raise ValueError(f"unknown precision {precision!r}; expected one of "
                        f"{sorted(_native.PRECISIONS)}")
@@ -85,6 +85,9 @@ class Engine:
     self.c_in_valid = _ceil(c_in + 3, 4)
     g = static_graph
     self.num_grid, self.num_mesh = g.num_grid_nodes, g.num_mesh_nodes
+    # Node-partitioned execution (partitioned.py): the local tables are [owned | halo]; node
+    # updates, aggregation and the decoder cover the owned rows only.  0 = every row is owned.
+    self.num_grid_owned, self.num_mesh_owned = int(num_grid_owned), int(num_mesh_owned)
     self._keep = []                       # device tensors referenced by raw pointer
     self._model = _native.Model()
     self._upload_graph(g)
@@ -106,10 +109,11 @@ class Engine:
   def _upload_graph(self, g: graph_lib.StaticGraph) -> None:
     m = self._model
     m.num_grid, m.num_mesh = g.num_grid_nodes, g.num_mesh_nodes
+    m.num_grid_owned, m.num_mesh_owned = self.num_grid_owned, self.num_mesh_owned
     # grid2mesh and multi-mesh edges in receiver-sorted execution order.
     p1, s1, r1, rp1 = graph_lib.receiver_sorted(g.g2m_senders, g.g2m_receivers, g.num_mesh_nodes)
     p2, s2, r2, rp2 = graph_lib.receiver_sorted(g.mesh_senders, g.mesh_receivers, g.num_mesh_nodes)
-    expected = np.repeat(np.arange(g.num_grid_nodes, dtype=np.int64), 3)
+    expected = np.repeat(np.arange(self.num_grid_owned or g.num_grid_nodes, dtype=np.int64), 3)
     if g.m2g_receivers.shape[0] != expected.shape[0] or not np.array_equal(
         g.m2g_receivers.astype(np.int64), expected):
       raise ValueError("mesh2grid edges must be grouped by grid node with fan-in 3")

@@ -121,7 +121,7 @@ class GraphCast(Predictor):
                params: Optional[Mapping[str, Mapping[str, np.ndarray]]] = None,
                precision: str = "bf16x3", device: Optional[Any] = None,
                pregather: bool = True, fuse: bool = True, chain_lag: int = 0,
-               image_residual: bool = False):
+               image_residual: bool = True, deep_chains: bool = True):
     if model_config.latent_size != engine_lib.LATENT:
       raise ValueError(f"latent_size {model_config.latent_size} is not supported by the "
                        f"sm_100a kernels (only {engine_lib.LATENT})")
@@ -132,6 +132,7 @@ class GraphCast(Predictor):
     self._precision = precision
     self._pregather = pregather
     self._fuse, self._chain_lag, self._image_residual = fuse, chain_lag, image_residual
+    self._deep_chains = deep_chains
     self._device = device
     self._params = params
     self._num_outputs = num_outputs(task_config)
@@ -187,7 +188,8 @@ class GraphCast(Predictor):
           self._static_graph, self._params, c_in=c_in, n_out=self._num_outputs,
           msg_steps=self._model_config.gnn_msg_steps, precision=self._precision,
           device=self._device, pregather=self._pregather, fuse=self._fuse,
-          chain_lag=self._chain_lag, image_residual=self._image_residual)
+          chain_lag=self._chain_lag, image_residual=self._image_residual,
+          deep_chains=self._deep_chains)
     elif self._engine.c_in != c_in:
       raise ValueError(f"inputs+forcings stack to {c_in} channels but the model was "
                        f"built for {self._engine.c_in}")

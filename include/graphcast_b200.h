@@ -126,6 +126,13 @@ int64_t gcb_a_image_bytes(int64_t rows, int32_t k);
 int gcb_rows_to_image(const float* src, int32_t ld, int32_t fan, int64_t rows, int32_t k,
                       void* img, void* stream);
 
+/* dst[i, 0:width] = src[idx[i], 0:width] for i < n (fp32, width a multiple of 4).  Packs the
+ * boundary rows of a latent table into the contiguous send buffer of the per-step halo exchange
+ * of the node-partitioned processor (the reference's analogue: the all_gather in front of every
+ * sharded gather, utils/gather_scatter_ops.py:423). */
+int gcb_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, int64_t n, float* dst,
+                    int32_t ld_dst, int32_t width, void* stream);
+
 int gcb_abi_version(void);
 const char* gcb_last_error(void);
 
@@ -405,7 +412,7 @@ int gcb_set_graph_replay(int32_t enabled);
  * Not thread safe. */
 typedef enum {
   GCB_KIND_LAYER_TC = 0, GCB_KIND_SEGMENT_SUM = 1, GCB_KIND_PACK = 2, GCB_KIND_UNPACK = 3,
-  GCB_KIND_LAYER_SIMT = 4, GCB_KIND_ROWS_TO_IMAGE = 5, GCB_KIND_CHAIN_TC = 6
+  GCB_KIND_LAYER_SIMT = 4, GCB_KIND_ROWS_TO_IMAGE = 5, GCB_KIND_CHAIN_TC = 6, GCB_KIND_GATHER = 7
 } gcb_kernel_kind;
 int gcb_profile_begin(void);
 int gcb_profile_end(int32_t capacity, int32_t* kinds, float* ms, double* flops, double* bytes,

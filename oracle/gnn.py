@@ -117,23 +117,33 @@ class Oracle:
       inter.update(vg0=vg0, vm0=vm0, e1=e1, m1=m1, agg1=agg1, vm1=vm1, vg1=vg1)
     return vm1, vg1
 
+  def processor_embed(self, graph: Mapping[str, np.ndarray], batch: int = 1):
+    """Embedded multi-mesh edge latents (the mesh GNN's `_embed`, deep_typed_graph_net.py:250-271)."""
+    bcast = lambda f: self._t(f)[:, None, :].expand(-1, batch, -1)
+    return self.mlp(mlp_name("mesh_gnn", "encoder_edges_", "mesh"), [bcast(graph["mesh_edge_feats"])])
+
+  def processor_step(self, graph: Mapping[str, np.ndarray], v, e, k: int):
+    """One InteractionNetwork step with node and edge residuals (deep_typed_graph_net.py:372-393):
+    returns (v_new, e_new)."""
+    g = "mesh_gnn"
+    s2, r2 = self._idx(graph["mesh_senders"]), self._idx(graph["mesh_receivers"])
+    m = self.mlp(mlp_name(g, f"processor_edges_{k}_", "mesh"), [e, v[s2], v[r2]])
+    agg = self.segment_sum(m, r2, v.shape[0])
+    v_new = v + self.mlp(mlp_name(g, f"processor_nodes_{k}_", "mesh_nodes"), [v, agg])
+    return v_new, e + m
+
+  def num_message_steps(self) -> int:
+    k = 0
+    while mlp_name("mesh_gnn", f"processor_edges_{k}_", "mesh") + "_mlp/~/linear_0" in self.p:
+      k += 1
+    return k
+
   def processor(self, graph: Mapping[str, np.ndarray], vm1, inter: Optional[dict] = None):
     """mesh_gnn (graphcast.py:606-639): all message-passing steps on the multi-mesh."""
     v = self._t(vm1)
-    batch = v.shape[1]
-    bcast = lambda f: self._t(f)[:, None, :].expand(-1, batch, -1)
-    n_mesh = v.shape[0]
-    g = "mesh_gnn"
-    e = self.mlp(mlp_name(g, "encoder_edges_", "mesh"), [bcast(graph["mesh_edge_feats"])])
-    s2, r2 = self._idx(graph["mesh_senders"]), self._idx(graph["mesh_receivers"])
-    k = 0
-    while mlp_name(g, f"processor_edges_{k}_", "mesh") + "_mlp/~/linear_0" in self.p:
-      m = self.mlp(mlp_name(g, f"processor_edges_{k}_", "mesh"), [e, v[s2], v[r2]])
-      agg = self.segment_sum(m, r2, n_mesh)
-      v_new = v + self.mlp(mlp_name(g, f"processor_nodes_{k}_", "mesh_nodes"), [v, agg])
-      e = e + m
-      v = v_new
-      k += 1
+    e = self.processor_embed(graph, v.shape[1])
+    for k in range(self.num_message_steps()):
+      v, e = self.processor_step(graph, v, e, k)
     if inter is not None:
       inter.update(v_mesh=v, e_mesh=e)
     return v

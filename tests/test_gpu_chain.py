@@ -272,7 +272,8 @@ def test_fused_step_is_bit_identical_to_the_layer_by_layer_step(prec):
   xt = torch.as_tensor(x)
   a = engine.Engine(g, params, c_in=31, n_out=23, msg_steps=3, precision=prec, fuse=False)
   ya = a.forward_features(xt).clone()
-  b = engine.Engine(g, params, c_in=31, n_out=23, msg_steps=3, precision=prec, fuse=True)
+  b = engine.Engine(g, params, c_in=31, n_out=23, msg_steps=3, precision=prec, fuse=True,
+                    image_residual=False)
   yb = b.forward_features(xt).clone()
   assert torch.equal(ya, yb)
   assert torch.equal(a.mesh_lat, b.mesh_lat) and torch.equal(a.grid_lat, b.grid_lat)
@@ -341,9 +342,10 @@ def test_image_residual_step_stays_within_the_parity_gate(msg_steps):
   g, params, x = _cases.small_case(c_in=31, n_out=23, msg_steps=msg_steps, batch=1)
   ref = oracle_gnn.Oracle(params, torch.float64).forward(g.as_dict(), x).numpy()
   xt = torch.as_tensor(x)
-  a = engine.Engine(g, params, c_in=31, n_out=23, msg_steps=msg_steps, precision="bf16x3")
+  a = engine.Engine(g, params, c_in=31, n_out=23, msg_steps=msg_steps, precision="bf16x3",
+                    image_residual=False)
   b = engine.Engine(g, params, c_in=31, n_out=23, msg_steps=msg_steps, precision="bf16x3",
-                    image_residual=True)
+                    image_residual=True, deep_chains=False)
   ya, yb = a.forward_features(xt).cpu().numpy(), b.forward_features(xt).cpu().numpy()
   ea = float(np.abs(ya - ref).max() / np.abs(ref).max())
   eb = float(np.abs(yb - ref).max() / np.abs(ref).max())

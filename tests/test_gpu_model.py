@@ -31,19 +31,20 @@ def test_step_matches_oracle(prec, tol, pregather):
   assert np.isfinite(y).all()
   assert _rel(y, ref) <= tol
   n_mlp = 6 + 1 + 2 * 3 + 4
-  # every MLP is one fused launch except the decoder's (n = 256 output); the fp32 validation arm
-  # always runs layer by layer
-  mlp_layers = 2 * n_mlp if prec == "fp32_simt" else (n_mlp - 1) + 2
-  projections = 2 * (1 + 3 + 1) if pregather else 0       # two per edge MLP (g2m, 3 mesh steps, m2g)
-  to_image = 1                          # summed m2g messages (the mesh aggregates' images are
-                                        # written by the segment-sum kernel itself)
-  assert eng.launches_per_step == mlp_layers + projections + (1 + 3) + to_image   # + segment sums
+  if prec == "fp32_simt":           # the fp32 validation arm always runs layer by layer
+    launches = 2 * n_mlp + (2 * (1 + 3 + 1) if pregather else 0) + (1 + 3) + 1
+  elif pregather:                   # deep chains: 6 (encoder) + 3 per message step + 5 (decoder)
+    launches = 6 + 3 * 3 + 5
+  else:                             # two-layer chains (the decoder's n = 256 output MLP: two launches)
+    launches = (n_mlp - 1) + 2 + (1 + 3) + 1
+  assert eng.launches_per_step == launches
 
 
 def test_stagewise_intermediates_match_oracle():
   g, params, x = _cases.small_case(c_in=31, n_out=23, msg_steps=2)
   _, inter = oracle_gnn.Oracle(params, torch.float64).forward(g.as_dict(), x, return_intermediates=True)
-  eng = engine.Engine(g, params, c_in=31, n_out=23, msg_steps=2, precision="bf16x3")
+  eng = engine.Engine(g, params, c_in=31, n_out=23, msg_steps=2, precision="bf16x3",
+                      image_residual=False)      # fp32 masters: readable intermediates
   eng.forward_features(torch.as_tensor(x))
   torch.cuda.synchronize()
   assert _rel(eng.mesh_lat.cpu().numpy(), inter["v_mesh"][:, 0].numpy()) < 5e-5
