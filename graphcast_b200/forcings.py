@@ -254,3 +254,38 @@ def get_toa_incident_solar_radiation_device(
         c_lon.data_ptr(), s_lon.data_ptr(), lat.shape[0], lon.shape[0], out.data_ptr(),
         torch.cuda.current_stream(dev).cuda_stream), "gcb_toa_incident_solar_radiation")
   return out
+
+
+def device_forcings(names: Sequence[str], datetimes: np.ndarray, dt_dims: Sequence[str],
+                    latitude: np.ndarray, longitude: np.ndarray, device=None) -> xs.Dataset:
+  """The named forcing variables for the given target datetimes, generated ON THE DEVICE: the
+  [lat, lon] field `toa_incident_solar_radiation` by the CUDA kernel (4 MB per timestamp at 0.25
+  degree, nothing crosses PCIe), the progress features (a few scalars / one value per longitude
+  per timestamp, data_utils.py:51-130) on the host and uploaded (KBs).  Used by
+  `rollout.chunked_prediction_generator(..., generate_forcings=...)` so that a long rollout needs no
+  per-step forcing transfer.  `datetimes` has dims `dt_dims` = ([batch,] time)."""
+  import torch
+  dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+  dt_dims = tuple(dt_dims)
+  dts = np.asarray(datetimes)
+  out = xs.Dataset()
+  names = list(names)
+  seconds = get_seconds_since_epoch(dts)
+  progress: Dict[str, Tuple[Tuple[str, ...], np.ndarray]] = {}
+  if any(n.startswith(YEAR_PROGRESS) for n in names):
+    progress.update(featurize_progress(YEAR_PROGRESS, dt_dims, get_year_progress(seconds)))
+  if any(n.startswith(DAY_PROGRESS) for n in names):
+    progress.update(featurize_progress(DAY_PROGRESS, dt_dims + ("lon",),
+                                       get_day_progress(seconds, np.asarray(longitude))))
+  for n in names:
+    if n == TISR:
+      field = get_toa_incident_solar_radiation_device(dts.reshape(-1), latitude, longitude, device=dev)
+      out[n] = xs.DataArray(field.reshape(tuple(dts.shape) + tuple(field.shape[1:])),
+                            dt_dims + ("lat", "lon"))
+    elif n in progress:
+      dims, vals = progress[n]
+      out[n] = xs.DataArray(torch.as_tensor(np.ascontiguousarray(vals, np.float32)).to(dev), dims)
+    else:
+      raise ValueError(f"cannot generate forcing variable {n!r} (known: {TISR}, "
+                       f"{YEAR_PROGRESS}*, {DAY_PROGRESS}*)")
+  return out

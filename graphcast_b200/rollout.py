@@ -112,8 +112,15 @@ def chunked_prediction_generator(
     num_steps_per_chunk: int, forcings=None, verbose: bool = False,
     pmap_devices: Optional[Sequence[Any]] = None, replica_axis: Optional[str] = None,
     device_put_fn: Optional[Callable] = None, replicate_fn: Optional[Callable] = None,
+    generate_forcings: Optional[Sequence[str]] = None,
 ) -> Iterator[xs.Dataset]:
-  """Yields the predictions of each chunk (device-resident)."""
+  """Yields the predictions of each chunk (device-resident).
+
+  `generate_forcings` (extension; the reference expects every forcing precomputed in `forcings`,
+  data_utils.py:51-215): names of forcing variables to generate on the device for every chunk from
+  the targets' `datetime` / `lat` / `lon` coordinates -- `toa_incident_solar_radiation` by the CUDA
+  kernel, the year / day progress features on the host (KBs) -- so that a long rollout uploads no
+  forcing fields at all."""
   if pmap_devices is not None and replica_axis is None:
     raise ValueError("Must provide replica_axis when pmap_devices is provided.")
   if (replicate_fn is None) ^ (replica_axis is None):
@@ -127,6 +134,12 @@ def chunked_prediction_generator(
   forcings = xs.from_xarray(forcings)
 
   inputs, targets_template, forcings = inputs.copy(), targets_template.copy(), forcings.copy()
+  if generate_forcings:
+    if "datetime" not in targets_template.coords:
+      raise ValueError("generate_forcings needs the `datetime` coordinate of the targets template")
+    gen_dims, gen_datetime = targets_template.coords["datetime"]
+    gen_lat = np.asarray(targets_template.coords["lat"][1])
+    gen_lon = np.asarray(targets_template.coords["lon"][1])
   inputs.coords.pop("datetime", None)
   output_datetime = targets_template.coords.pop("datetime", None)
   forcings.coords.pop("datetime", None)
@@ -159,6 +172,12 @@ def chunked_prediction_generator(
     target_slice = slice(lo, lo + num_steps_per_chunk)
     current_targets_template = targets_template.isel(time=target_slice)
     current_forcings = forcings.isel(time=target_slice)
+    if generate_forcings:
+      from graphcast_b200 import forcings as forcings_lib
+      idx = tuple(target_slice if d == "time" else slice(None) for d in gen_dims)
+      generated = forcings_lib.device_forcings(generate_forcings, np.asarray(gen_datetime)[idx], gen_dims,
+                                               gen_lat, gen_lon)
+      current_forcings = current_forcings.assign(generated)
     time_coords_to_override = {n: c for n, c in current_targets_template.coords.items()
                                if "time" in c[0]}
     if replicate_fn is not None:

@@ -163,3 +163,32 @@ def test_device_resident_rollout_matches_step_chain():
     assert _rel(got, want) <= 2e-4, k
     pred = model_utils.stacked_to_dataset(want, t_k)
     cur = rollout._get_next_inputs(cur, pred.assign(f_k)).assign_coords(time=inputs.coords["time"][1])
+
+
+def test_rollout_with_device_generated_forcings_matches_host_forcings():
+  """`generate_forcings`: TISR by the CUDA kernel + progress features per chunk, no forcing fields
+  uploaded, against the same rollout fed with the host (numpy) mirror of the reference's forcing
+  generation (data_utils.py:51-215, solar_radiation.py:443-521; pinned in
+  tests/test_reference_forcings_golden.py)."""
+  from graphcast_b200 import forcings as forcings_lib
+  task, (inputs, template, forcings) = _task_example(batch=1, steps=3)
+  t0 = np.datetime64("2021-03-17T06:00:00")
+  datetime = (t0 + np.asarray(template.coords["time"][1])).astype("datetime64[ns]")[None, :]   # [batch, time]
+  template = template.assign_coords(datetime=(("batch", "time"), datetime))
+  host = xs.Dataset(coords=dict(template.coords))
+  forcings_lib.add_derived_vars(host)
+  forcings_lib.add_tisr_var(host)
+  host_forcings = xs.Dataset({k: host.data_vars[k] for k in task.forcing_variables},
+                             coords={k: c for k, c in forcings.coords.items()})
+  cfg = graphcast.ModelConfig(10.0, 2, 512, 2, 1, 0.6)
+  params = oracle_gnn.init_params(c_in=synthetic.num_input_channels(task), n_out=83, msg_steps=2, seed=4)
+  model = graphcast.GraphCast(cfg, task, params=params)
+  fn = lambda rng, inputs, targets_template, forcings: model(inputs, targets_template, forcings)
+  # the synthetic inputs' own forcing channels are N(0,1); scale the generated TISR (1e6 J/m^2) likewise
+  a = rollout.chunked_prediction(fn, None, inputs, template, host_forcings)
+  b = rollout.chunked_prediction(fn, None, inputs, template, None,
+                                 generate_forcings=list(task.forcing_variables))
+  for name in a.data_vars:
+    x, y = np.asarray(a.data_vars[name].values), np.asarray(b.data_vars[name].values)
+    assert np.isfinite(y).all()
+    assert np.abs(x - y).max() <= 2e-4 * max(1.0, np.abs(x).max()), name

@@ -37,6 +37,22 @@ torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 out["config3_rollout_40_steps"] = {"steps": n, "seconds_per_10_day_forecast": dt, "steps_per_s": n / dt,
                                    "note": "chunked_prediction_generator, device-resident state, forcings H2D per step"}
+# same rollout with the forcings generated on the device (TISR kernel + progress features): no forcing upload
+t_dt = (np.datetime64("2021-03-17T06:00:00") + np.asarray(template.coords["time"][1])).astype("datetime64[ns]")[None, :]
+template_dt = template.assign_coords(datetime=(("batch", "time"), t_dt))
+gen = list(task.forcing_variables)
+next(iter(rollout.chunked_prediction_generator(fn, None, inputs, rollout.extend_targets_template(template_dt, 1), 1, None, generate_forcings=gen)))
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+n = 0
+for chunk in rollout.chunked_prediction_generator(fn, None, inputs, template_dt, 1, None, generate_forcings=gen):
+  n += 1
+  del chunk
+torch.cuda.synchronize()
+dt = time.perf_counter() - t0
+out["config3_rollout_40_steps_device_forcings"] = {
+    "steps": n, "seconds_per_10_day_forecast": dt, "steps_per_s": n / dt,
+    "note": "forcings generated per step on the device (gcb_toa_incident_solar_radiation + progress features)"}
 # bf16 mode at config 2
 planes = m._planes_in[0]
 eng = m.engine
