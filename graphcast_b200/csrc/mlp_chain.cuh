@@ -258,6 +258,7 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
     const uint32_t a_bytes = Cfg::kAStageBytes;
     const uint32_t a_half = a_bytes / 2;
     uint32_t stage = 0, phase = 0, tu = 0;
+    const uint64_t keep_policy = ptx::l2_policy_evict_last();
     for (int st = 0; st < nsteps; ++st) {
       for (int li = 0; li < L; ++li) {
         const int l = desc ? L - 1 - li : li;
@@ -272,6 +273,7 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
           const ChainSeg sg = s_seg[l * 3 + s];
           const uint8_t* a_ptr = nullptr;
           bool a_copy = false;
+          const bool a_scratch = sg.src_q >= 0;
           if (sg.src_q >= 0) {
             const long long w0 = tr ? clock64() : 0;
             // Poll at CTA scope (a cluster-scope acquire per retry is far more expensive), then
@@ -295,7 +297,9 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
             uint8_t* a_dst = stage_base + stage * Cfg::kStageBytes;
             if (ptx::elect_one()) {
               ptx::mbar_arrive_expect_tx(&full_bar[stage], tx);
-              if (a_copy)
+              if (a_scratch)
+                ptx::bulk_g2s_multicast_hint(a_dst + crank * a_half, a_ptr, a_half, &full_bar[stage], cmask, keep_policy);
+              else if (a_copy)
                 ptx::bulk_g2s_multicast(a_dst + crank * a_half, a_ptr, a_half, &full_bar[stage], cmask);
               ptx::bulk_g2s(a_dst + Cfg::kAStageBytes, b_ptr, b_bytes, &full_bar[stage]);
             }
@@ -374,6 +378,7 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
     const int rsub = lane >> 3;
     const int col_base = static_cast<int>(crank) * kUnitN;   // my 256 columns of every layer
     uint32_t g_count = 0, ln_count = 0, u = 0;
+    const uint64_t keep_policy = ptx::l2_policy_evict_last();
 
     // Per-unit context, passed BY VALUE: as mutable locals captured by reference these lived in
     // local memory and every use in the chunk loops was an LDL on the critical path.
@@ -595,9 +600,9 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
                 *reinterpret_cast<uint4*>(img0 + o) = make_uint4(h0.x, h0.y, h1.x, h1.y);
                 *reinterpret_cast<uint4*>(img0 + o + kAPartBytes) = make_uint4(l0.x, l0.y, l1.x, l1.y);
               }
-              if (img1 != nullptr) {
-                *reinterpret_cast<uint4*>(img1 + o) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-                *reinterpret_cast<uint4*>(img1 + o + kAPartBytes) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+              if (img1 != nullptr) {       // scratch slot: keep these lines in the L2
+                ptx::st_global_v4_hint(img1 + o, make_uint4(h0.x, h0.y, h1.x, h1.y), keep_policy);
+                ptx::st_global_v4_hint(img1 + o + kAPartBytes, make_uint4(l0.x, l0.y, l1.x, l1.y), keep_policy);
               }
             }
           }

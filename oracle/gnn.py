@@ -183,6 +183,20 @@ class Oracle:
     return out
 
 
+class Bf16OperandOracle(Oracle):
+  """The product's "bf16" mode, emulated: every contraction takes its two operands rounded to
+  bfloat16 (round-to-nearest-even) and accumulates in this oracle's dtype; everything else
+  (bias, swish, LayerNorm, residuals, aggregation) stays in that dtype.  This is what
+  `precision="bf16"` / `casting.Bfloat16Cast` computes on the device (one tensor-core product per MAC,
+  fp32 accumulation, latents as 2 x bf16) -- NOT the reference's all-bf16 execution, where XLA also
+  rounds every activation, the LayerNorm and (outside grid2mesh) the aggregation to bf16
+  (utils/casting.py:31-65, graphcast.py:215,232,260); see graphcast_b200/casting.py."""
+
+  def matmul(self, x, w):
+    r = lambda t: t.to(torch.float32).to(torch.bfloat16).to(self.dtype)
+    return r(x) @ r(w)
+
+
 def truncated_normal(rng: np.random.Generator, shape, stddev: float) -> np.ndarray:
   """hk.initializers.TruncatedNormal: N(0,1) truncated to [-2,2], times stddev."""
   x = rng.standard_normal(shape)

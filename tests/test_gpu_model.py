@@ -192,3 +192,42 @@ def test_rollout_with_device_generated_forcings_matches_host_forcings():
     x, y = np.asarray(a.data_vars[name].values), np.asarray(b.data_vars[name].values)
     assert np.isfinite(y).all()
     assert np.abs(x - y).max() <= 2e-4 * max(1.0, np.abs(x).max()), name
+
+
+def test_bf16_mode_matches_its_emulation():
+  """precision="bf16" (what casting.Bfloat16Cast selects) is a defined arithmetic: every contraction
+  takes both operands rounded to bfloat16 and accumulates in fp32.
+    * per layer that is exact: device vs the fp64 product of the bf16-rounded operands <= 2e-6;
+    * over a whole step a bf16-rounded pipeline is DISCONTINUOUS -- the fp32 and the fp64 evaluation of
+      the same emulation already differ by 3e-3 rms (rounding decisions flip), which is the point made
+      in casting.py about comparing two bf16 implementations -- so the step-level statement is
+      statistical: the device is as far from the fp64 emulation as the fp32 emulation is (x1.5), and its
+      error against the exact step has the emulation's size (x0.5 .. x1.5)."""
+  import ctypes as C
+  import test_gpu_chain as tc
+  from graphcast_b200 import _native
+  lib = _native.lib()
+  gen = torch.Generator().manual_seed(1)
+  rows = 128 * 40 + 3
+  a = torch.randn(rows, 512, generator=gen)
+  layer = tc.Layer(lib, 512, 512, gen, ln=False)
+  out = torch.full((rows, 512), float("nan"), device="cuda:0")
+  img = tc._image(lib, a.to("cuda:0"), rows, 512)
+  tc._layer_forward(lib, "bf16", rows, [tc._seg_img(img, 512)], layer, act=False, out=out)
+  torch.cuda.synchronize()
+  r = lambda t: t.to(torch.bfloat16).double()
+  want = r(a) @ r(layer.w) + layer.bias.double()
+  assert float((out.cpu().double() - want).abs().max() / want.abs().max()) <= 2e-6
+
+  g, params, x = _cases.small_case(c_in=31, n_out=23, msg_steps=3, batch=1)
+  emu64 = oracle_gnn.Bf16OperandOracle(params, torch.float64).forward(g.as_dict(), x).numpy()
+  emu32 = oracle_gnn.Bf16OperandOracle(params, torch.float32).forward(g.as_dict(), x).numpy()
+  ref = oracle_gnn.Oracle(params, torch.float64).forward(g.as_dict(), x).numpy()
+  eng = engine.Engine(g, params, c_in=31, n_out=23, msg_steps=3, precision="bf16")
+  y = eng.forward_features(torch.as_tensor(x)).cpu().numpy()
+  rms = lambda p, q: float(np.sqrt(np.mean((p - q) ** 2)) / np.sqrt(np.mean(q ** 2)))
+  d_emu, e_emu, d_ref, e_ref = rms(y, emu64), rms(emu32, emu64), rms(y, ref), rms(emu64, ref)
+  print(f"bf16 mode, rms: device vs emulation {d_emu:.2e} (fp32 vs fp64 emulation {e_emu:.2e}); "
+        f"device vs exact {d_ref:.2e} (emulation vs exact {e_ref:.2e})")
+  assert d_emu <= 1.5 * e_emu
+  assert 0.5 * e_ref <= d_ref <= 1.5 * e_ref

@@ -13,7 +13,9 @@ with open(path, newline="") as f:
   lines = [l for l in f if not l.startswith("==")]
 for r in csv.DictReader(lines):
   name = r.get("Kernel Name", "")
-  if "gcb::" not in name:
+  if not any(k in name for k in ("mlp_chain_tc_kernel", "mlp_layer_tc_kernel", "mlp_layer_simt_kernel",
+                                  "segment_sum_kernel", "pack_grid", "unpack_grid", "rows_to_image_kernel",
+                                  "gather_rows_kernel", "tisr_kernel")):
     continue
   k = int(r["ID"])
   d = rows.setdefault(k, {"name": name})

@@ -65,7 +65,7 @@ def case(kind):
   scratch = tc._scratch(lib, 1, lag, 1)
   ch = _native.ChainDesc()
   ch.rows, ch.nlayers, ch.precision, ch.lag = rows, 2, 0, lag
-  ch.scratch = scratch.data_ptr()
+  ch.scratch, ch.scratch_bytes = scratch.data_ptr(), scratch.numel()
   tc._fill_chain_layer(ch.layer[0], segs, [-1] * len(segs), l0, act=True, keep=True, pre=pre)
   if IMG_RES:     # latent as image only: residual read back from the image, updated in place
     img2.copy_(tc._image(lib, res, rows, 512))
