@@ -10,8 +10,9 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)),
-                         "libgraphcast_b200.so")
+# GCB_LIB: an alternative build of the same library (kernel experiments); default = the in-tree one.
+_LIB_PATH = os.environ.get("GCB_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                      "libgraphcast_b200.so")
 
 GCB_ABI_VERSION = 2
 GCB_MAX_MSG_STEPS = 64

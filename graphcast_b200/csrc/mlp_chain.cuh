@@ -41,6 +41,19 @@ namespace gcb {
 constexpr int kChainSlotsMax = 5;
 constexpr int kScratchTileBytes = (kMaxN / kKStep) * GCB_A_IMAGE_BLOCK;   // 32 x 8448 = 270336
 constexpr int kChainTailBytes = 3072;
+// Epilogue warpgroups.  The epilogue is the critical path of every unit and is bound by
+// instruction latency (one warp per scheduler: ncu source view, profiles/r02_ncu_full_chain_*): two
+// warpgroups (warps 4-7 and 8-11) take alternate 32-column chunks of the unit's accumulator, warp w
+// and w + 4 sharing a TMEM lane quarter.  Warps 12-15 gather the pre-activation addends (chunk c ->
+// staging buffer c & 1 -> epilogue group c & 1); fp32-table segments are produced by the otherwise
+// idle warps 2-3 of the issue warpgroup.
+#ifndef GCB_EPI_GROUPS
+#define GCB_EPI_GROUPS 2
+#endif
+constexpr int kEpiGroups = GCB_EPI_GROUPS;
+constexpr int kGatherGroups = 3 - kEpiGroups;                  // producer warpgroups left: 1 or 2
+constexpr int kATableWarps = 2;                                // warps 2 and 3
+static_assert(kEpiGroups == 1 || kEpiGroups == 2, "one or two epilogue warpgroups");
 
 // kBig: room for 8 instead of 4 [512]-float parameter vectors (biases, LayerNorm scale / offset):
 // chains of two MLPs; costs 8 KB of shared memory (one operand stage in some variants).
@@ -53,9 +66,13 @@ struct ChainConfig {
   static constexpr int kParamBytes = kParamVecs * kMaxN * 4;
   static constexpr int kGRegionBytes = kPre ? kGBytes : 0;
   static constexpr int kFixedBytes =
-      kParamBytes + kEpiStageBytes + kGRegionBytes + kLnxBytes + kChainTailBytes;
+      kParamBytes + kEpiGroups * kEpiStageBytes + kGRegionBytes + kEpiGroups * kLnxBytes + kChainTailBytes;
   static constexpr int kFit = (kSmemLimit - kFixedBytes) / kStageBytes;
+#ifdef GCB_FORCE_STAGES          // experiment: sensitivity of a launch to the ring depth
+  static constexpr int kStages = GCB_FORCE_STAGES < kFit ? GCB_FORCE_STAGES : kFit;
+#else
   static constexpr int kStages = kFit < 12 ? kFit : 12;
+#endif
   static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
   static_assert(kStages >= 4, "operand ring too shallow");
 };
@@ -94,24 +111,24 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* stage_base = smem;
   float* s_param = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  float* s_epi = s_param + Cfg::kParamBytes / 4;                    // [4][32][36]
-  float* s_g = s_epi + 4 * 32 * kEpiRowFloats;                      // [2][128][36] (kPre only)
-  float2* s_lnx = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(s_g) + Cfg::kGRegionBytes);
-  uint8_t* tail = reinterpret_cast<uint8_t*>(s_lnx) + kLnxBytes;
+  float* s_epi = s_param + Cfg::kParamBytes / 4;                    // [kEpiGroups][4][32][36]
+  float* s_g = s_epi + kEpiGroups * 4 * 32 * kEpiRowFloats;         // [2][128][36] (kPre only)
+  float2* s_lnx = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(s_g) + Cfg::kGRegionBytes);  // [kEpiGroups][2][128]
+  uint8_t* tail = reinterpret_cast<uint8_t*>(s_lnx) + kEpiGroups * kLnxBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);          // [12]
   uint64_t* empty_bar = full_bar + 12;                             // [12]
   uint64_t* tmem_full_bar = empty_bar + 12;                        // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;                    // [2]
   uint64_t* g_full_bar = tmem_empty_bar + 2;                       // [2]
   uint64_t* g_empty_bar = g_full_bar + 2;                          // [2]
-  uint64_t* lnx_bar = g_empty_bar + 2;                             // [2]
-  uint64_t* h_full_bar = lnx_bar + 2;                              // [GCB_MAX_CHAIN][kChainSlotsMax]
+  uint64_t* lnx_bar = g_empty_bar + 2;                             // [kEpiGroups][2]
+  uint64_t* h_full_bar = lnx_bar + 4;                              // [GCB_MAX_CHAIN][kChainSlotsMax]
   uint64_t* h_free_bar = h_full_bar + GCB_MAX_CHAIN * kChainSlotsMax;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(h_free_bar + GCB_MAX_CHAIN * kChainSlotsMax);
   ChainLayer* s_layer = reinterpret_cast<ChainLayer*>(tmem_base_slot + 2);           // [4]
   ChainSeg* s_seg = reinterpret_cast<ChainSeg*>(s_layer + GCB_MAX_CHAIN);            // [4][3]
   PreAddInfo* s_pre = reinterpret_cast<PreAddInfo*>(s_seg + GCB_MAX_CHAIN * 3);      // [4][2]
-  static_assert((2 * 12 + 10 + 2 * GCB_MAX_CHAIN * kChainSlotsMax) * 8 + 8 +
+  static_assert((2 * 12 + 12 + 2 * GCB_MAX_CHAIN * kChainSlotsMax) * 8 + 8 +
                     GCB_MAX_CHAIN * (sizeof(ChainLayer) + 3 * sizeof(ChainSeg) + 2 * sizeof(PreAddInfo))
                     <= kChainTailBytes, "tail region too small");
 
@@ -213,20 +230,20 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
       }
     }
     for (int s = 0; s < Cfg::kStages; ++s) {
-      ptx::mbar_init(&full_bar[s], any_table ? 5 : 1);   // TMA lane (+ 4 A-producer warps)
+      ptx::mbar_init(&full_bar[s], any_table ? 1 + kATableWarps : 1);   // TMA lane (+ the A-table warps)
       ptx::mbar_init(&empty_bar[s], 2);                   // tcgen05.commit of both CTAs
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tmem_full_bar[b], 1);
-      ptx::mbar_init(&tmem_empty_bar[b], 4);
-      ptx::mbar_init(&g_full_bar[b], 4);
-      ptx::mbar_init(&g_empty_bar[b], 4);
-      ptx::mbar_init(&lnx_bar[b], 1);
+      ptx::mbar_init(&tmem_empty_bar[b], 4 * kEpiGroups);   // every epilogue warp
+      ptx::mbar_init(&g_full_bar[b], 4);        // the 4 warps of the gather group that filled it
+      ptx::mbar_init(&g_empty_bar[b], 4);       // the 4 warps of the epilogue group that read it
+      for (int eg = 0; eg < kEpiGroups; ++eg) ptx::mbar_init(&lnx_bar[eg * 2 + b], 1);
     }
     for (int l = 0; l < L; ++l) {
       if (q_of_layer[l] < 0) continue;
       for (int sl = 0; sl < nslots; ++sl) {
-        ptx::mbar_init(&h_full_bar[q_of_layer[l] * kChainSlotsMax + sl], 8);
+        ptx::mbar_init(&h_full_bar[q_of_layer[l] * kChainSlotsMax + sl], 8 * kEpiGroups);
         ptx::mbar_init(&h_free_bar[q_of_layer[l] * kChainSlotsMax + sl],
                        2 * (consumers[l] > 0 ? consumers[l] : 1));
       }
@@ -247,9 +264,13 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
   // Register re-allocation per warpgroup (setmaxnreg): the epilogue is the critical path of
   // every unit and, at the 128 registers a 512-thread CTA starts with, it spills its residual /
   // staging values to local memory inside the chunk loops; the issue warps need a fraction of
-  // that.  56 x 4 + 216 x 4 + 112 x 8 warps = 1984 <= 2048 register slices of the SM.
+  // that.  One epilogue group: 56 x 4 + 216 x 4 + 112 x 8 warps = 1984; two: 72 x 4 + 176 x 8 +
+  // 88 x 4 = 2048 of the 2048 register slices of the SM.
+  constexpr int kRegsCtl = kEpiGroups == 2 ? 72 : 56;
+  constexpr int kRegsEpi = kEpiGroups == 2 ? 176 : 216;
+  constexpr int kRegsProd = kEpiGroups == 2 ? 88 : 112;
   if (warp < 4) {
-    ptx::setmaxnreg_dec<56>();
+    ptx::setmaxnreg_dec<kRegsCtl>();
   if (warp == 0) {
     // ===== TMA warp (converged; every lane polls, one elected lane issues) =====
     const uint32_t b_bytes = Cfg::kBStageBytes;
@@ -367,13 +388,84 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
         ++u;
       }
     }
+  } else if (any_table) {
+    // ===== A-table warps (2 and 3): segments given as fp32 tables =====
+    // Gather through the segment's index, optional fan-in sum, split to bf16 hi / lo, store in
+    // the UMMA K-major core-matrix layout.  They arrive on EVERY K-step's full barrier (for image
+    // / scratch K-steps without writing anything), so the barrier count is uniform.
+    const int t64 = threadIdx.x - 64;
+    const int sub = t64 & 3;                        // which float4 of the 16-wide K-step
+    const int rg = t64 >> 2;                        // 0..15; rows rg + 16*i
+    const uint32_t sts_off = (sub >> 1) * kALbo + (sub & 1) * 8;
+    uint32_t stage = 0, phase = 0;
+    for (int st = 0; st < nsteps; ++st) {
+      for (int li = 0; li < L; ++li) {
+        const int l = desc ? L - 1 - li : li;
+        const int ti = st - l * lag;
+        if (ti < 0 || ti >= T) continue;
+        const uint32_t tile = cid + static_cast<uint32_t>(ti) * ncl;
+        const int nseg = s_layer[l].nseg;
+        for (int s = 0; s < nseg; ++s) {
+          const ChainSeg sg = s_seg[l * 3 + s];
+          const bool is_tab = sg.src_q < 0 && sg.img == nullptr;
+          int src[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            src[i] = -1;
+            if (is_tab) {
+              const long long grow = static_cast<long long>(tile) * kTileM + rg + 16 * i;
+              if (grow < rows_total) src[i] = sg.idx ? __ldg(sg.idx + grow) : static_cast<int>(grow);
+            }
+          }
+          for (int k = 0; k < sg.ksteps; ++k) {
+            float4 cur[8];
+            if (is_tab) {
+              const int koff = k * kKStep + sub * 4;
+              const bool kvalid = koff < sg.k_valid;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kvalid && src[i] >= 0) {
+                  const float* p = sg.table + static_cast<long long>(src[i]) * sg.fan * sg.ld + koff;
+                  acc = __ldg(reinterpret_cast<const float4*>(p));
+                  for (int j = 1; j < sg.fan; ++j) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(p + static_cast<long long>(j) * sg.ld));
+                    acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+                  }
+                }
+                cur[i] = acc;
+              }
+            }
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (is_tab) {
+              uint8_t* a_hi = stage_base + stage * Cfg::kStageBytes;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                uint2 hi, lo;
+                ptx::split_bf16x4(cur[i], hi, lo);
+                const uint32_t off = sts_off + (rg + 16 * i) * 16;
+                *reinterpret_cast<uint2*>(a_hi + off) = hi;
+                if (kSplit) *reinterpret_cast<uint2*>(a_hi + kAPartBytes + off) = lo;
+              }
+              ptx::fence_proxy_async_smem();
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&full_bar[stage]);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
   }
-  } else if (warp < 8) {
+  } else if (warp < 4 + 4 * kEpiGroups) {
     // ===== epilogue =====
-    ptx::setmaxnreg_inc<216>();
-    const int ew = warp - 4;
+    ptx::setmaxnreg_inc<kRegsEpi>();
+    const int eg = (warp - 4) >> 2;               // epilogue group: chunks with (chunk & 1) == eg
+    const int ew = warp & 3;                      // TMEM lane quarter
     const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
-    float* my_epi = s_epi + ew * 32 * kEpiRowFloats;
+    float* my_epi = s_epi + (eg * 4 + ew) * 32 * kEpiRowFloats;
+    float2* my_lnx = s_lnx + eg * 2 * kTileM;     // [2][128] of this group
+    uint64_t* my_lnx_bar = lnx_bar + eg * 2;
     const int cg = lane & 7;
     const int rsub = lane >> 3;
     const int col_base = static_cast<int>(crank) * kUnitN;   // my 256 columns of every layer
@@ -437,10 +529,11 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
           }
         }
       };
-      load_res(0);
-      const bool trp = cx.trace_u >= 0 && ew == 0 && lane == 0;
+      constexpr int kChunkStep = 32 * kEpiGroups;          // my chunks: eg, eg + kEpiGroups, ...
+      load_res(32 * eg);
+      const bool trp = cx.trace_u >= 0 && ew == 0 && lane == 0 && eg == 0;
       long long t_ld = 0, t_math = 0, t_f32 = 0, t_img = 0;
-      for (int c0 = 0; c0 < kUnitN; c0 += 32) {
+      for (int c0 = 32 * eg; c0 < kUnitN; c0 += kChunkStep) {
         const int gc0 = col_base + c0;
         const int col = gc0 + cg * 4;
         float v[32];
@@ -456,8 +549,10 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
           for (int j = 0; j < 32; ++j) v[j] += b[j];
         }
         if (kPre && !is_ln && n_pre > 0) {
-          const uint32_t gb = g_count & 1;
-          ptx::mbar_wait(&g_full_bar[gb], (g_count >> 1) & 1);
+          // staging buffer = chunk parity; with two epilogue groups that is my group index and
+          // every fill of that buffer is mine
+          const uint32_t gb = kEpiGroups == 2 ? static_cast<uint32_t>(eg) : (g_count & 1);
+          ptx::mbar_wait(&g_full_bar[gb], (kEpiGroups == 2 ? g_count : (g_count >> 1)) & 1);
           const float* gp = s_g + gb * kGBufFloats + (ew * 32 + lane) * kEpiRowFloats;
           float g[32];
 #pragma unroll
@@ -610,7 +705,7 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
         // Next chunk's residual: requested once this chunk's values are dead (no extra registers);
         // the line is already in L2 (prefetched a step ahead), so the TMEM load and LayerNorm
         // math of the next chunk cover its latency.
-        if (c0 + 32 < kUnitN) load_res(c0 + 32);
+        if (c0 + kChunkStep < kUnitN) load_res(c0 + kChunkStep);
         if (trp) { const long long t = clock64(); t_img += t - tp; tp = t; }
       }
       if (trp) {
@@ -670,7 +765,7 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
         // this tile (same threads, same rows and columns: program order makes it visible, and the
         // slot cannot be rewritten before these warps reach tile ti + nslots themselves).
         if (cl.res_q >= 0) cx.res_img = scratch_slot(cl.res_q, ti);
-        if (ti + 1 < T && (cl.residual != nullptr || cl.res_img != nullptr)) {
+        if (eg == 0 && ti + 1 < T && (cl.residual != nullptr || cl.res_img != nullptr)) {
           // Pull the residual of this layer's NEXT tile into L2 now (a whole step ahead).
           const uint32_t ntile = tile + ncl;
           if (cl.residual != nullptr) {
@@ -689,13 +784,13 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
           const long long w0 = tracing(u) ? clock64() : 0;
           ptx::mbar_wait(&h_free_bar[keep_q * kChainSlotsMax + (ti % nslots)],
                          (static_cast<uint32_t>(ti / nslots) & 1u) ^ 1u);
-          if (ew == 0 && lane == 0) trace_val(u, 9, clock64() - w0);
+          if (ew == 0 && lane == 0 && eg == 0) trace_val(u, 9, clock64() - w0);
           cx.img1 = scratch_slot(keep_q, ti);
         }
         const uint32_t buf = u & 1;
         ptx::mbar_wait(&tmem_full_bar[buf], (u >> 1) & 1);
         ptx::tc_fence_after_sync();
-        if (ew == 0 && lane == 0) trace(u, 3);
+        if (ew == 0 && lane == 0 && eg == 0) trace(u, 3);
         const uint32_t taddr = tmem_base + lane_base + buf * kUnitN;
         if (kind >= kKindLN) {
           const uint32_t lb = ln_count & 1, par = (ln_count >> 1) & 1;
@@ -704,16 +799,18 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
           const float mean_h = shift + s1 * (1.0f / kUnitN);
           const float m2_h = fmaxf(s2 - s1 * s1 * (1.0f / kUnitN), 0.f);
           const int myrow = ew * 32 + lane;
-          ptx::st_async_f32x2(ptx::mapa(ptx::smem_addr(&s_lnx[lb * kTileM + myrow]), peer), mean_h, m2_h,
-                              ptx::mapa(ptx::smem_addr(&lnx_bar[lb]), peer));
-          if (ew == 0 && lane == 0) ptx::mbar_arrive_expect_tx(&lnx_bar[lb], kTileM * 8);
-          ptx::mbar_wait(&lnx_bar[lb], par);
-          const float2 other = s_lnx[lb * kTileM + myrow];
+          // (with two epilogue groups both compute the statistics of all 256 columns and run
+          // their own exchange with the same group of the partner CTA: no coupling between groups)
+          ptx::st_async_f32x2(ptx::mapa(ptx::smem_addr(&my_lnx[lb * kTileM + myrow]), peer), mean_h, m2_h,
+                              ptx::mapa(ptx::smem_addr(&my_lnx_bar[lb]), peer));
+          if (ew == 0 && lane == 0) ptx::mbar_arrive_expect_tx(&my_lnx_bar[lb], kTileM * 8);
+          ptx::mbar_wait(&my_lnx_bar[lb], par);
+          const float2 other = my_lnx[lb * kTileM + myrow];
           const float delta = other.x - mean_h;
           const float mean = 0.5f * (mean_h + other.x);
           const float var = (m2_h + other.y + delta * delta * (0.5f * kUnitN)) * (1.0f / (2 * kUnitN));
           const float rstd = rsqrtf(var + 1e-5f);
-          if (ew == 0 && lane == 0) trace(u, 4);
+          if (ew == 0 && lane == 0 && eg == 0) trace(u, 4);
           if (kind == kKindLNRes)
             g_count = finish_unit(std::integral_constant<int, kKindLNRes>{}, cx, g_count, taddr, row0, mean, rstd);
           else if (kind == kKindLNImg)
@@ -726,7 +823,7 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
         } else {
           g_count = finish_unit(std::integral_constant<int, kKindPlain>{}, cx, g_count, taddr, row0, 0.f, 1.f);
         }
-        if (ew == 0 && lane == 0) trace(u, 5);
+        if (ew == 0 && lane == 0 && eg == 0) trace(u, 5);
         // accumulator free for the MMA warp
         ptx::tc_fence_before_sync();
         __syncwarp();
@@ -742,26 +839,20 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
             ptx::mbar_arrive_remote(ptx::mapa(ptx::smem_addr(hb), peer));
           }
         }
-        if (ew == 0 && lane == 0) trace(u, 10);
+        if (ew == 0 && lane == 0 && eg == 0) trace(u, 10);
         ++u;
       }
     }
   } else {
-    // ===== producers =====
-    ptx::setmaxnreg_dec<112>();
-    const int group = (warp - 8) >> 2;
-    const int tid_g = threadIdx.x - 256 - group * 128;
-    const int sub = tid_g & 3;
-    const int rg = tid_g >> 2;
-    const uint32_t sts_off = (sub >> 1) * kALbo + (sub & 1) * 8;
-    // Roles: with fp32-table segments somewhere in the chain both groups share the A K-steps
-    // (group g owns the K-steps with it % 2 == g), unless there are also pre-activation
-    // addends - then group 0 produces A and group 1 gathers.  Without table segments both
-    // groups gather (alternating 32-column chunks).
-    const bool do_gather = kPre && (!any_table || group == 1);
-    const bool do_a = any_table && !do_gather;
-    const bool a_all = any_table && kPre;            // group 0 owns every K-step
-    if (do_gather) {
+    // ===== gather warps: pre-activation addends of the split edge MLP =====
+    ptx::setmaxnreg_dec<kRegsProd>();
+    const int first_warp = 4 + 4 * kEpiGroups;
+    const int group = (warp - first_warp) >> 2;        // 0 (.. 1 with a single epilogue group)
+    const int tid_g = threadIdx.x - 32 * first_warp - group * 128;
+    if (kPre) {
+      // Thread (rp, cgp): rows rp + 16*p (p < 8), 16-byte column group cgp of each 32-column
+      // chunk: 8 lanes read one 128-byte line segment of a gathered row.  Chunk c goes to staging
+      // buffer c & 1; with two gather groups group g fills the chunks of its parity.
       const int cgp = tid_g & 7, rp = tid_g >> 3;
       uint32_t gc = 0;
       const int gcol_lo = static_cast<int>(crank) * kUnitN, gcol_hi = gcol_lo + kUnitN;
@@ -791,7 +882,7 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
           }
           for (int c0 = gcol_lo; c0 < gcol_hi; c0 += 32, ++gc) {
             const uint32_t gb = gc & 1;
-            if (!any_table && gb != static_cast<uint32_t>(group)) continue;
+            if (kGatherGroups == 2 && gb != static_cast<uint32_t>(group)) continue;
             float4 acc[8];
 #pragma unroll
             for (int p = 0; p < 8; ++p)
@@ -813,85 +904,6 @@ mlp_chain_tc_kernel(const __grid_constant__ gcb_chain_desc d, const int nq, cons
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&g_full_bar[gb]);
           }
-        }
-      }
-    } else if (do_a) {
-      uint32_t it = 0;                               // global K-step counter (ring position)
-      for (int st = 0; st < nsteps; ++st) {
-        for (int li = 0; li < L; ++li) {
-          const int l = desc ? L - 1 - li : li;
-          const int ti = st - l * lag;
-          if (ti < 0 || ti >= T) continue;
-          const uint32_t tile = cid + static_cast<uint32_t>(ti) * ncl;
-          const int nseg = s_layer[l].nseg;
-          float4 cur[4];
-          bool have_cur = false, cur_img = false;
-          uint32_t cur_it = 0;
-          // Software pipeline over the K-steps this group owns: the loads of the next owned
-          // K-step are in flight while the current one is converted and stored.
-          auto flush = [&]() {
-            const uint32_t stage = cur_it % Cfg::kStages;
-            const uint32_t phase = (cur_it / Cfg::kStages) & 1;
-            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* a_hi = stage_base + stage * Cfg::kStageBytes;
-            if (!cur_img) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                uint2 hi, lo;
-                ptx::split_bf16x4(cur[i], hi, lo);
-                const uint32_t off = sts_off + (rg + 32 * i) * 16;
-                *reinterpret_cast<uint2*>(a_hi + off) = hi;
-                if (kSplit) *reinterpret_cast<uint2*>(a_hi + kAPartBytes + off) = lo;
-              }
-            }
-            ptx::fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&full_bar[stage]);
-            have_cur = false;
-          };
-          for (int s = 0; s < nseg; ++s) {
-            const ChainSeg sg = s_seg[l * 3 + s];
-            const bool is_tab = sg.src_q < 0 && sg.img == nullptr;
-            long long src[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              src[i] = -1;
-              if (is_tab) {
-                const long long grow = static_cast<long long>(tile) * kTileM + rg + 32 * i;
-                if (grow < rows_total) src[i] = sg.idx ? static_cast<long long>(__ldg(sg.idx + grow)) : grow;
-              }
-            }
-            for (int k = 0; k < sg.ksteps; ++k, ++it) {
-              const bool mine = a_all || (it & 1u) == static_cast<uint32_t>(group);
-              if (!mine) continue;
-              float4 nxt[4] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f),
-                               make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
-              if (is_tab) {
-                const int koff = k * kKStep + sub * 4;
-                const bool kvalid = koff < sg.k_valid;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (kvalid && src[i] >= 0) {
-                    const float* p = sg.table + src[i] * sg.fan * sg.ld + koff;
-                    acc = __ldg(reinterpret_cast<const float4*>(p));
-                    for (int j = 1; j < sg.fan; ++j) {
-                      const float4 t = __ldg(reinterpret_cast<const float4*>(p + static_cast<long long>(j) * sg.ld));
-                      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-                    }
-                  }
-                  nxt[i] = acc;
-                }
-              }
-              if (have_cur) flush();
-#pragma unroll
-              for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
-              cur_it = it;
-              cur_img = !is_tab;
-              have_cur = true;
-            }
-          }
-          if (have_cur) flush();
         }
       }
     }

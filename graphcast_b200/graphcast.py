@@ -223,7 +223,8 @@ class GraphCast(Predictor):
     # (reference _inputs_to_grid_node_features :680-699; dataset_to_stacked order).
     buf = self._call_index % 2
     self._call_index += 1
-    if self._planes_bufs[buf] is None or self._planes_bufs[buf].shape != (batch, c_in, eng.num_grid):
+    fresh = self._planes_bufs[buf] is None or self._planes_bufs[buf].shape != (batch, c_in, eng.num_grid)
+    if fresh:
       self._planes_bufs[buf] = torch.empty([batch, c_in, eng.num_grid], dtype=torch.float32,
                                            device=eng.device)
       self._buf_free[buf] = None
@@ -242,6 +243,12 @@ class GraphCast(Predictor):
       if self._h2d_stream is None:
         self._h2d_stream = torch.cuda.Stream(device=eng.device)
       copy_stream = self._h2d_stream
+      if fresh:
+        # The caching allocator may hand back a block whose previous user still has kernels
+        # queued on the compute stream: order the first copy after them, and tell the allocator
+        # that the copy stream uses this block too.
+        copy_stream.wait_stream(compute)
+        planes_in.record_stream(copy_stream)
       if self._buf_free[buf] is not None:
         copy_stream.wait_event(self._buf_free[buf])      # kernels of call k-2 are done with it
     else:
