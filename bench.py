@@ -602,6 +602,65 @@ def run_partitioned(args):
     dist.destroy_process_group()
 
 
+def run_rollout(args):
+  """BASELINE config 3: an N-step autoregressive rollout through the public API
+  (`rollout.chunked_prediction_generator`): device-resident state (the next inputs are assembled on
+  the GPU), forcings generated per step on the device (TISR kernel + progress features), every
+  prediction copied to pinned host memory.  value = forecast steps per second over the rollout."""
+  import torch
+  from graphcast_b200 import graphcast, rollout, synthetic
+  rank, world, local = dist_env()
+  if rank != 0:
+    return
+  torch.cuda.set_device(local)
+  dev = torch.device(f"cuda:{local}")
+  res, mesh, task_name = WORKLOADS[args.workload]
+  task = getattr(graphcast, task_name)
+  cfg = graphcast.ModelConfig(resolution=res, mesh_size=mesh, latent_size=512, gnn_msg_steps=16,
+                              hidden_layers=1, radius_query_fraction_edge_length=0.6)
+  c_in = synthetic.num_input_channels(task)
+  n = args.rollout
+  inputs, template, _ = synthetic.make_example(task, res, num_target_steps=n, seed=0, pinned=True)
+  dt = (np.datetime64("2021-03-17T06:00:00") + np.asarray(template.coords["time"][1])).astype("datetime64[ns]")[None, :]
+  template = template.assign_coords(datetime=(("batch", "time"), dt))
+  params = graphcast.init_params(cfg, task, c_in, seed=1)
+  model = graphcast.GraphCast(cfg, task, params=params, precision=args.precision, device=dev)
+  fn = lambda rng, inputs, targets_template, forcings: model(inputs, targets_template, forcings)
+  gen = list(task.forcing_variables)
+  host = None
+
+  def run(template_n):
+    nonlocal host
+    count = 0
+    for chunk in rollout.chunked_prediction_generator(fn, None, inputs, template_n, 1, None,
+                                                      generate_forcings=gen):
+      if host is None:
+        host = {k: torch.empty(v.shape, dtype=torch.float32, pin_memory=True)
+                for k, v in chunk.data_vars.items()}
+      for k, v in chunk.data_vars.items():
+        host[k].copy_(v.data, non_blocking=True)
+      count += 1
+    torch.cuda.synchronize()
+    return count
+
+  run(rollout.extend_targets_template(template, 2))          # warm-up: graph build, first replays
+  t0 = time.perf_counter()
+  steps = run(template)
+  secs = time.perf_counter() - t0
+  d2h = sum(int(np.prod(v.shape)) * 4 for v in host.values())
+  line = {
+      "metric": "6h-step forecasts/sec", "value": steps / secs, "unit": "steps/s", "n_gpus": 1,
+      "steps": steps, "warmup": 2, "ms_per_step": secs / steps * 1e3, "higher_is_better": True,
+      "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+      "config": {"workload": args.workload + f"_rollout{steps}", "mode": "rollout",
+                 "seconds_per_rollout": secs,
+                 "note": "rollout.chunked_prediction_generator: device-resident state, forcings "
+                         "generated on the device, predictions D2H every step (wall clock)"},
+      "e2e": {"value": steps / secs, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h},
+  }
+  print(json.dumps(line), flush=True)
+
+
 def main():
   # Exactly one JSON line may reach stdout: libraries (NCCL's version banner, warnings) are
   # diverted to stderr by pointing fd 1 at fd 2 for the duration of the run.
@@ -618,6 +677,8 @@ def main():
                   help="partitioned (default for N > 1): ONE forecast over all GPUs, mesh-node partition "
                        "+ NCCL halo exchange per message-passing step (strong scaling); replicas: one "
                        "independent forecast per GPU, no collective (weak scaling)")
+  ap.add_argument("--rollout", type=int, default=0,
+                  help="BASELINE config 3: time an N-step autoregressive rollout through the public API")
   ap.add_argument("--check", action="store_true",
                   help="partitioned mode: compare the gathered output with the single-GPU step")
   ap.add_argument("--workload", choices=sorted(WORKLOADS), default=DEFAULT_WORKLOAD)
@@ -641,6 +702,8 @@ def main():
   args = ap.parse_args()
   if args.impl == "reference":
     run_reference(args)
+  elif args.rollout > 0:
+    run_rollout(args)
   elif args.mode == "partitioned" or (args.mode == "auto" and dist_env()[1] > 1):
     run_partitioned(args)
   else:
