@@ -250,8 +250,15 @@ def extend_targets_template(targets_template, required_num_steps: int,
   coords["time"] = (("time",), extended_time)
   if "datetime" in targets_template.coords:
     dims, vals = targets_template.coords["datetime"]
-    first = np.asarray(vals).reshape(-1)[0]
-    coords["datetime"] = (("time",), (first - timestep) + extended_time)
+    vals = np.asarray(vals)
+    if tuple(dims) == ("time",):
+      coords["datetime"] = (("time",), (vals[0] - timestep) + extended_time)
+    else:                                   # ([batch,] time): every batch element keeps its own start
+      t_axis = tuple(dims).index("time")
+      first = np.take(vals, [0], axis=t_axis)
+      shape = [1] * vals.ndim
+      shape[t_axis] = required_num_steps
+      coords["datetime"] = (tuple(dims), (first - timestep) + extended_time.reshape(shape))
   out = xs.Dataset(coords=coords)
   fill = 0.0 if value is None else value
   for name, v in targets_template.data_vars.items():
