@@ -109,7 +109,7 @@ def test_config2_quarter_degree_stagewise_matches_the_oracle():
   # ---- encoder -------------------------------------------------------------------------
   eng.run_stage("encode")
   torch.cuda.synchronize()
-  vm1 = eng.mesh_lat.cpu().numpy()                      # [Nm, 512]
+  vm1 = eng.mesh_rows_in_reference_order(eng.mesh_lat).cpu().numpy()   # [Nm, 512], reference node ids
   deg = np.bincount(g.g2m_receivers, minlength=g.num_mesh_nodes)
   assert deg.max() == 3753
   mesh_rows = np.unique(np.concatenate([np.argsort(deg)[-24:], rng.choice(g.num_mesh_nodes, 300, False)]))
@@ -128,7 +128,7 @@ def test_config2_quarter_degree_stagewise_matches_the_oracle():
   for k in range(16):
     eng.run_stage("process_step", k)
   torch.cuda.synchronize()
-  v_gpu = eng.mesh_lat.cpu().numpy()
+  v_gpu = eng.mesh_rows_in_reference_order(eng.mesh_lat).cpu().numpy()
   v_ref = orc.processor(g.as_dict(), vm1[:, None, :])[:, 0].numpy()
   e_proc = _rel(v_gpu, v_ref)
   print(f"config 2 processor (16 steps, 327 660 edges, in full, from the GPU's encoder output): {e_proc:.3e}")

@@ -47,7 +47,7 @@ def test_stagewise_intermediates_match_oracle():
                       image_residual=False)      # fp32 masters: readable intermediates
   eng.forward_features(torch.as_tensor(x))
   torch.cuda.synchronize()
-  assert _rel(eng.mesh_lat.cpu().numpy(), inter["v_mesh"][:, 0].numpy()) < 5e-5
+  assert _rel(eng.mesh_rows_in_reference_order(eng.mesh_lat).cpu().numpy(), inter["v_mesh"][:, 0].numpy()) < 5e-5
   assert _rel(eng.grid_lat.cpu().numpy(), inter["vg2"][:, 0].numpy()) < 5e-5
 
 
@@ -231,3 +231,14 @@ def test_bf16_mode_matches_its_emulation():
         f"device vs exact {d_ref:.2e} (emulation vs exact {e_ref:.2e})")
   assert d_emu <= 1.5 * e_emu
   assert 0.5 * e_ref <= d_ref <= 1.5 * e_ref
+
+
+def test_internal_mesh_numbering_is_invisible():
+  """The device numbers the mesh nodes along a space-filling curve (gather locality); the step output
+  must be bit-identical to the run with the reference's numbering."""
+  g, params, x = _cases.small_case(c_in=31, n_out=23, msg_steps=3, batch=1)
+  xt = torch.as_tensor(x)
+  a = engine.Engine(g, params, c_in=31, n_out=23, msg_steps=3, precision="bf16x3", reorder_mesh=False)
+  b = engine.Engine(g, params, c_in=31, n_out=23, msg_steps=3, precision="bf16x3", reorder_mesh=True)
+  assert b.mesh_order is not None and sorted(b.mesh_order.tolist()) == list(range(g.num_mesh_nodes))
+  assert torch.equal(a.forward_features(xt), b.forward_features(xt))
