@@ -20,7 +20,7 @@ Haiku-default random weights.  Prints ONE JSON line on rank 0.
              direct launches); `hbm` gives every kernel's achieved GB/s and fraction of the
              measured copy bandwidth; `traffic` is read from the committed ncu launch list.
   cpu_baseline / --impl reference : the fp32 CPU oracle (torch-CPU) on a bounded sample of the
-             SAME workload: a contiguous block of 1/32 of the rows of every stage of the real
+             SAME workload: a contiguous block of 1/16 of the rows of every stage of the real
              0.25 degree graph (oracle/sampled_step.py), scaled by the row fraction.
 """
 
@@ -683,7 +683,7 @@ def main():
                   help="partitioned mode: compare the gathered output with the single-GPU step")
   ap.add_argument("--workload", choices=sorted(WORKLOADS), default=DEFAULT_WORKLOAD)
   ap.add_argument("--precision", choices=["bf16x3", "bf16", "fp32_simt"], default="bf16x3")
-  ap.add_argument("--cpu-fraction", dest="cpu_fraction", type=float, default=1.0 / 32,
+  ap.add_argument("--cpu-fraction", dest="cpu_fraction", type=float, default=1.0 / 16,
                   help="row fraction of every stage of the workload the CPU sample runs")
   ap.add_argument("--profile-steps", dest="profile_steps", type=int, default=5)
   ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=10)
