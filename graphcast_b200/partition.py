@@ -25,10 +25,11 @@ This module builds that plan with numpy only:
   NCCL on GPUs, gloo in the CPU tests): one `all_to_all_single`-equivalent built
   from batched isend / irecv so that it also runs on gloo.
 
-The CUDA engine is not wired to this plan yet (round 2); `tests/test_partition.py`
-checks the plan's invariants, the halo sizes quoted above, and - with the CPU
-oracle on 2 gloo ranks - that the partitioned processor reproduces the
-single-rank processor.
+`graphcast_b200/partitioned.py` (round 2) builds on the same bisection and ownership
+rule for the WHOLE step on GPUs (all three graphs, grid nodes, NCCL exchange);
+`tests/test_partition.py` checks this module's plan invariants, the halo sizes quoted
+above, and - with the CPU oracle on 2 gloo ranks - that the partitioned processor
+reproduces the single-rank processor.
 """
 
 from __future__ import annotations

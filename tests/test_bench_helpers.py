@@ -29,3 +29,17 @@ def test_thread_candidates(bench):
   assert bench.thread_candidates(128) == [32, 16]        # the oversubscribed 128-thread pass is skipped
   assert bench.thread_candidates(8) == [8]
   assert bench.thread_candidates(48) == [48, 32, 16]
+
+
+def test_ncu_traffic_reads_the_committed_launch_list():
+  import bench
+  tc, src = bench.ncu_traffic(bench.DEFAULT_WORKLOAD, "bf16x3")
+  assert tc is not None and 100e9 < tc < 250e9           # tensor-core kernels: DRAM bytes per step
+  assert "r02_launches_ncu.csv" in src
+  assert bench.ncu_traffic("graphcast_small_1deg_13lvl", "bf16x3") == (None, None)
+
+
+def test_algorithmic_flops_match_the_survey():
+  import bench
+  f = bench.algorithmic_flops(1038240, 40962, 1618818, 327660, 3114720, 471, 227, 16)
+  assert abs(f / 1e12 - 29.29) < 0.01
