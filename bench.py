@@ -490,7 +490,8 @@ def run_partitioned(args):
                                     radius_query_fraction_edge_length=0.6)
   params = graphcast.init_params(cfg, task, c_in, seed=1)
   pe = partitioned.PartitionedEngine(g, params, c_in=c_in, n_out=n_out, msg_steps=16, rank=rank,
-                                     world=world, device=dev, precision=args.precision)
+                                     world=world, device=dev, precision=args.precision,
+                                     image_residual=args.image_residual)
   lg = pe.local
   gen = torch.Generator(device=dev).manual_seed(0)          # same full field on every rank
   planes_full = torch.randn(c_in, g.num_grid_nodes, device=dev, generator=gen)
@@ -549,6 +550,53 @@ def run_partitioned(args):
   one_step()                                               # restore a valid state for --check
   torch.cuda.synchronize()
 
+  # Per-kernel profile of rank 0 (separate pass: an event pair around every launch of the C ABI).
+  lib = _native.lib()
+  prof_steps = max(1, min(args.steps, args.profile_steps))
+  cap = 512 * prof_steps
+  lib.gcb_profile_begin()
+  for _ in range(prof_steps):
+    one_step()
+  torch.cuda.synchronize()
+  kinds = (C.c_int32 * cap)(); kms = (C.c_float * cap)()
+  kfl = (C.c_double * cap)(); kby = (C.c_double * cap)(); cnt = C.c_int32(0)
+  _native.check(lib.gcb_profile_end(cap, kinds, kms, kfl, kby, C.byref(cnt)), "profile_end")
+  launches_per_step = cnt.value // prof_steps
+  tc_ms = sum(kms[i] for i in range(min(cnt.value, cap)) if kinds[i] in (0, 6)) / prof_steps
+
+  # End to end: every step uploads this rank's input planes from pinned host memory and downloads
+  # its share of the predictions to pinned host memory (both inside the timed region).
+  host_in = torch.empty(planes_local.shape, dtype=torch.float32, pin_memory=True)
+  host_in.copy_(planes_local)
+  host_out = torch.empty(planes_out.shape, dtype=torch.float32, pin_memory=True)
+  dev_in = torch.empty_like(planes_local)
+
+  def e2e_step():
+    dev_in.copy_(host_in, non_blocking=True)
+    pe.step(dev_in)
+    with pe.engine._on_device():
+      _native.check(pe._lib.gcb_unpack_grid_outputs(
+          pe.engine.grid_out.data_ptr(), 256, n_out, n_owned, None, None, None, None,
+          planes_out.data_ptr(), pe.engine._stream()), "gcb_unpack_grid_outputs")
+    host_out.copy_(planes_out, non_blocking=True)
+
+  e2e_steps = max(2, min(args.steps, args.e2e_steps))
+  e2e_step()
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  t0 = time.perf_counter()
+  for _ in range(e2e_steps):
+    e2e_step()
+  torch.cuda.synchronize()
+  e2e = torch.tensor([(time.perf_counter() - t0) * 1e3 / e2e_steps], dtype=torch.float64, device=dev)
+  io = torch.tensor([host_in.numel() * 4, host_out.numel() * 4], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    dist.all_reduce(io, op=dist.ReduceOp.SUM)
+  one_step()                                               # valid state again for --check
+  torch.cuda.synchronize()
+
   check = None
   if args.check:
     # partitioned output (gathered) against the single-GPU step with the same kernels
@@ -567,7 +615,7 @@ def run_partitioned(args):
       del pe
       torch.cuda.empty_cache()
       eng = engine.Engine(g, params, c_in=c_in, n_out=n_out, msg_steps=16, precision=args.precision,
-                          device=dev, image_residual=False, deep_chains=False)
+                          device=dev, image_residual=args.image_residual, deep_chains=False)
       eng.pack_inputs(planes_full)
       eng.step()
       torch.cuda.synchronize()
@@ -579,6 +627,12 @@ def run_partitioned(args):
         err = max(err, float((parts[r][:ids.numel(), :n_out] - full[ids]).abs().max()) / scale)
       check = {"max_abs_rel_err_vs_single_gpu": err, "bitwise_equal": err == 0.0}
 
+  alg_flops = algorithmic_flops(g.num_grid_nodes, g.num_mesh_nodes, len(g.g2m_senders),
+                                len(g.mesh_senders), len(g.m2g_senders), c_in, n_out, 16)
+  try:
+    peak_tf = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1400.0)
+  except Exception:
+    peak_tf = 1400.0
   if rank == 0:
     st = partitioned.plan_statistics(g, world) if world > 1 else None
     line = {
@@ -590,12 +644,29 @@ def run_partitioned(args):
                    "parallelism": f"one forecast over {world} GPUs: mesh nodes by recursive coordinate "
                                   "bisection, edges owned by their receiver, grid nodes by containing "
                                   "triangle; 17 halo exchanges (NCCL all_to_all_v of fp32 rows) per step",
+                   "image_residual": bool(args.image_residual),
                    "ms_per_step_without_halo_exchange": float(h.item()),
                    "halo_exchange_ms_per_step": ms_per_step - float(h.item()),
                    "halo_exchanges_per_step": 17 if world > 1 else 0,
                    "partition": st},
         "clocks": clocks, "check": check,
-        "gpu_launches_per_step": None,
+        "e2e": {"value": 1e3 / float(e2e.item()), "unit": "steps/s", "ms_per_step": float(e2e.item()),
+                "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()),
+                "steps": e2e_steps,
+                "note": "every rank uploads its local input planes and downloads its owned prediction rows"},
+        "gpu_launches": launches_per_step * args.steps * world,
+        "gpu_launches_per_step": launches_per_step * world,
+        "gpu_launches_note": "kernels launched through the C ABI per forecast step, summed over ranks "
+                             "(rank 0 counted, x world); the NCCL all_to_all kernels come on top",
+        "roofline": {
+            "kernel": "gcb::mlp_chain_tc_kernel + gcb::mlp_layer_tc_kernel (fused tcgen05 layers), rank 0",
+            "bound": "tensor", "unit": "TFLOP/s",
+            "achieved": alg_flops / world / (max(tc_ms, 1e-9) * 1e-3) / 1e12, "peak": peak_tf,
+            "frac": alg_flops / world / (max(tc_ms, 1e-9) * 1e-3) / 1e12 / peak_tf,
+            "kernel_ms_per_step": tc_ms, "kernel_share_of_step": tc_ms / ms_per_step,
+            "traffic": None,
+            "note": "algorithmic FLOPs of the whole step / ranks, over rank 0's tensor-core kernel time"},
+        "cpu_baseline": None,
     }
     print(json.dumps(line), flush=True)
   if world > 1:

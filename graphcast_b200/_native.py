@@ -118,6 +118,8 @@ EXPORTS = {
     "gcb_a_image_bytes": (C.c_int64, [C.c_int64, C.c_int32]),
     "gcb_rows_to_image": (C.c_int, [_fp, C.c_int32, C.c_int32, C.c_int64, C.c_int32, _fp, _fp]),
     "gcb_gather_rows": (C.c_int, [_fp, C.c_int32, _fp, C.c_int64, _fp, C.c_int32, C.c_int32, _fp]),
+    "gcb_image_rows_pack": (C.c_int, [_fp, _fp, C.c_int64, _fp, _fp]),
+    "gcb_image_rows_unpack": (C.c_int, [_fp, C.c_int64, _fp, C.c_int64, _fp]),
     "gcb_pack_weight_host": (C.c_int, [_fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _fp]),
     "gcb_layer_forward": (C.c_int, [C.POINTER(LayerDesc), _fp]),
     "gcb_segment_sum": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, _fp, C.c_int32, C.c_int32, _fp]),

@@ -799,6 +799,34 @@ int gcb_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, int64_
   return GCB_OK;
 }
 
+static int image_rows(bool to_image, void* img, const int32_t* idx, int64_t first_row, int64_t n,
+                      void* buf, void* stream) {
+  GCB_CHECK_ARG(n >= 0 && first_row >= 0, "bad row range");
+  if (n == 0) return GCB_OK;
+  GCB_CHECK_ARG(img && buf && (to_image || idx) && aligned16(img) && aligned16(buf),
+                "null/unaligned pointer");
+  long long blocks = (n + 7) / 8;
+  const long long cap = static_cast<long long>(sm_count_cached()) * 8;
+  if (blocks > cap) blocks = cap;
+  ProfScope prof(static_cast<cudaStream_t>(stream), GCB_KIND_GATHER, 0.0, 4096.0 * n);
+  if (to_image)
+    gcb::image_rows_kernel<true><<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<unsigned char*>(img), idx, first_row, n, static_cast<unsigned char*>(buf));
+  else
+    gcb::image_rows_kernel<false><<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<unsigned char*>(img), idx, first_row, n, static_cast<unsigned char*>(buf));
+  GCB_CUDA(cudaGetLastError());
+  return GCB_OK;
+}
+
+int gcb_image_rows_pack(const void* img, const int32_t* idx, int64_t n, void* buf, void* stream) {
+  return image_rows(false, const_cast<void*>(img), idx, 0, n, buf, stream);
+}
+
+int gcb_image_rows_unpack(const void* buf, int64_t n, void* img, int64_t first_row, void* stream) {
+  return image_rows(true, img, nullptr, first_row, n, const_cast<void*>(buf), stream);
+}
+
 int gcb_rows_to_image(const float* src, int32_t ld, int32_t fan, int64_t rows, int32_t k,
                       void* img, void* stream) {
   GCB_CHECK_ARG(src && img && aligned16(src) && aligned16(img), "null/unaligned pointer");

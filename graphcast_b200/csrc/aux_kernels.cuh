@@ -128,6 +128,37 @@ gather_rows_kernel(const float* __restrict__ src, int ld_src, const int* __restr
   }
 }
 
+// Rows of an operand image of a [*, 512] matrix <-> a dense buffer of 2048-byte packed rows (the
+// send / receive side of a halo exchange when the latent stream exists only as an image).  A packed
+// row holds, per (K-step, 8-column chunk) piece, the 16 bytes of bf16 "hi" then the 16 bytes of "lo"
+// exactly as the image stores them, so the receiver's image rows are the owner's bit for bit.
+// kToImage = false: buf[i] = image row idx[i];  true: image row first_row + i = buf[i].
+template <bool kToImage>
+__global__ void __launch_bounds__(256)
+image_rows_kernel(unsigned char* __restrict__ img, const int* __restrict__ idx, long long first_row,
+                  long long n, unsigned char* __restrict__ buf) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  for (long long i = warp; i < n; i += nwarps) {
+    const long long row = kToImage ? first_row + i : static_cast<long long>(idx[i]);
+    unsigned char* tile = img + static_cast<size_t>(row >> 7) * 32 * 8448 + (row & 127) * 16;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int piece = lane + 32 * h;              // (K-step, chunk) = (piece >> 1, piece & 1)
+      unsigned char* p = tile + static_cast<size_t>(piece >> 1) * 8448 + (piece & 1) * 2112;
+      uint4* b = reinterpret_cast<uint4*>(buf + i * 2048 + piece * 32);
+      if (kToImage) {
+        *reinterpret_cast<uint4*>(p) = b[0];
+        *reinterpret_cast<uint4*>(p + 4224) = b[1];
+      } else {
+        b[0] = *reinterpret_cast<const uint4*>(p);
+        b[1] = *reinterpret_cast<const uint4*>(p + 4224);
+      }
+    }
+  }
+}
+
 // planes [n_ch, n_nodes] (+ node_static [n_nodes, n_static]) -> feats [n_nodes, ld],
 // feats[i, c] = (planes[c, i] - mean[c]) / scale[c]; 32x32 smem-tiled transpose so
 // both the plane reads (along nodes) and the feature writes (along channels) are

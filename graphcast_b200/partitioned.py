@@ -156,15 +156,19 @@ class PartitionedEngine:
   """One rank's share of one forecast: a local `Engine` + the per-step halo exchange."""
 
   def __init__(self, g: graph_lib.StaticGraph, params, *, c_in: int, n_out: int, msg_steps: int,
-               rank: int, world: int, device, precision: str = "bf16x3", group=None):
+               rank: int, world: int, device, precision: str = "bf16x3", group=None,
+               image_residual: bool = True):
     import torch
     from graphcast_b200 import _native, engine
     self.local = build_local_graph(g, world, rank)
     self.rank, self.world, self.group = rank, world, group
     lg = self.local
-    # fp32 masters next to the images: the halo rows travel as fp32 rows
+    # The halo rows travel as 2048-byte rows: fp32 rows gathered from the fp32 master, or -- image-only
+    # latents (default) -- the rows of the operand image themselves (bf16 hi + lo pieces), which the
+    # receiver stores into its own image unchanged.
+    self.image_residual = bool(image_residual)
     self.engine = engine.Engine(lg.graph, params, c_in=c_in, n_out=n_out, msg_steps=msg_steps,
-                                precision=precision, device=device, image_residual=False,
+                                precision=precision, device=device, image_residual=self.image_residual,
                                 deep_chains=False, num_grid_owned=int(lg.grid_owned.size),
                                 num_mesh_owned=int(lg.mesh_owned.size))
     eng = self.engine
@@ -174,7 +178,11 @@ class PartitionedEngine:
     self.send_rows = torch.as_tensor(lg.send_rows, dtype=torch.int32, device=eng.device)
     self.n_send, self.n_halo = int(lg.send_rows.size), int(lg.mesh_halo.size)
     self.send_buf = torch.empty([max(self.n_send, 1), 512], dtype=torch.float32, device=eng.device)
-    self.halo_view = eng.mesh_lat[lg.mesh_owned_pad:lg.mesh_owned_pad + self.n_halo]
+    if self.image_residual:
+      self.halo_view = torch.empty([max(self.n_halo, 1), 512], dtype=torch.float32,
+                                   device=eng.device)[:self.n_halo]
+    else:
+      self.halo_view = eng.mesh_lat[lg.mesh_owned_pad:lg.mesh_owned_pad + self.n_halo]
     self.skip_exchange = False      # measurement aid (bench.py): time a step without exchanges
     self._events = []
 
@@ -190,18 +198,28 @@ class PartitionedEngine:
       ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
       ev[0].record()
     with eng._on_device():
-      self._native.check(self._lib.gcb_gather_rows(
-          eng.mesh_lat.data_ptr(), 512, self.send_rows.data_ptr(), self.n_send,
-          self.send_buf.data_ptr(), 512, 512, eng._stream()), "gcb_gather_rows")
+      if self.image_residual:
+        self._native.check(self._lib.gcb_image_rows_pack(
+            eng.mesh_lat_img.data_ptr(), self.send_rows.data_ptr(), self.n_send,
+            self.send_buf.data_ptr(), eng._stream()), "gcb_image_rows_pack")
+      else:
+        self._native.check(self._lib.gcb_gather_rows(
+            eng.mesh_lat.data_ptr(), 512, self.send_rows.data_ptr(), self.n_send,
+            self.send_buf.data_ptr(), 512, 512, eng._stream()), "gcb_gather_rows")
     dist.all_to_all_single(self.halo_view, self.send_buf[:self.n_send],
                            output_split_sizes=lg.recv_counts, input_split_sizes=lg.send_counts,
                            group=self.group)
     if self.n_halo:
-      img_off = (lg.mesh_owned_pad // TILE) * 32 * 8448
       with eng._on_device():
-        self._native.check(self._lib.gcb_rows_to_image(
-            self.halo_view.data_ptr(), 512, 1, self.n_halo, 512,
-            eng.mesh_lat_img.data_ptr() + img_off, eng._stream()), "gcb_rows_to_image")
+        if self.image_residual:
+          self._native.check(self._lib.gcb_image_rows_unpack(
+              self.halo_view.data_ptr(), self.n_halo, eng.mesh_lat_img.data_ptr(),
+              lg.mesh_owned_pad, eng._stream()), "gcb_image_rows_unpack")
+        else:
+          img_off = (lg.mesh_owned_pad // TILE) * 32 * 8448
+          self._native.check(self._lib.gcb_rows_to_image(
+              self.halo_view.data_ptr(), 512, 1, self.n_halo, 512,
+              eng.mesh_lat_img.data_ptr() + img_off, eng._stream()), "gcb_rows_to_image")
     if ev is not None:
       ev[1].record()
       self._events.append(ev)

@@ -91,3 +91,42 @@ def test_pack_and_unpack_are_exact_transposes_with_affine():
   _native.check(lib.gcb_unpack_grid_outputs(y.data_ptr(), 256, n_out, n_nodes, None, None, None,
                                             None, out.data_ptr(), st), "unpack")
   assert torch.equal(out, y[:, :n_out].t().contiguous())
+
+
+def test_halo_row_packing_fp32_rows_and_image_rows():
+  """Send / receive side of the halo exchange (graphcast_b200/partitioned.py): gcb_gather_rows on an
+  fp32 table, and gcb_image_rows_pack / _unpack on an operand image -- the unpacked image rows must be
+  the packed rows' bytes (the receiver holds the owner's image rows bit for bit)."""
+  lib = _native.lib()
+  st = torch.cuda.current_stream().cuda_stream
+  g = torch.Generator().manual_seed(5)
+  rows, n = 1000, 333                                   # ragged: not multiples of the 128-row tile
+  x = torch.randn(rows, 512, generator=g).to("cuda:0")
+  idx = torch.randperm(rows, generator=g)[:n].to(torch.int32).to("cuda:0")
+  dense = torch.empty(n, 512, device="cuda:0")
+  _native.check(lib.gcb_gather_rows(x.data_ptr(), 512, idx.data_ptr(), n, dense.data_ptr(), 512, 512,
+                                    st), "gather_rows")
+  assert torch.equal(dense, x[idx.long()])
+
+  def image_of(t, r):
+    img = torch.zeros(lib.gcb_a_image_bytes(r, 512), dtype=torch.uint8, device="cuda:0")
+    _native.check(lib.gcb_rows_to_image(t.data_ptr(), 512, 1, r, 512, img.data_ptr(), st), "image")
+    return img
+
+  img = image_of(x, rows)
+  buf = torch.zeros(n, 2048, dtype=torch.uint8, device="cuda:0")
+  _native.check(lib.gcb_image_rows_pack(img.data_ptr(), idx.data_ptr(), n, buf.data_ptr(), st), "pack")
+  # receiver: rows 256.. of a second image (a halo block behind 256 owned rows)
+  first = 256
+  other = torch.randn(first + n, 512, generator=g).to("cuda:0")
+  img2 = image_of(other, first + n)
+  untouched = img2.clone()
+  _native.check(lib.gcb_image_rows_unpack(buf.data_ptr(), n, img2.data_ptr(), first, st), "unpack")
+  expect = image_of(torch.cat([other[:first], x[idx.long()]]), first + n)
+  torch.cuda.synchronize()
+  assert torch.equal(img2, expect)
+  tile0 = 32 * 8448 * (first // 128)
+  assert torch.equal(img2[:tile0], untouched[:tile0])   # owned tiles untouched
+  # n = 0 is a no-op, bad arguments are refused
+  assert lib.gcb_image_rows_pack(img.data_ptr(), idx.data_ptr(), 0, buf.data_ptr(), st) == 0
+  assert lib.gcb_image_rows_unpack(buf.data_ptr(), -1, img2.data_ptr(), 0, st) != 0
