@@ -165,6 +165,36 @@ def test_device_resident_rollout_matches_step_chain():
     cur = rollout._get_next_inputs(cur, pred.assign(f_k)).assign_coords(time=inputs.coords["time"][1])
 
 
+def test_pinned_prediction_sink_delivers_every_chunk():
+  """rollout.PinnedPredictionSink: side-stream copies of the device-resident chunks, overlapping the
+  next step, equal the trajectory `chunked_prediction` returns (rotating pinned slots, depth 2)."""
+  task, (inputs, template, forcings) = _task_example(batch=1, steps=4)
+  cfg = graphcast.ModelConfig(10.0, 2, 512, 2, 1, 0.6)
+  params = oracle_gnn.init_params(c_in=synthetic.num_input_channels(task), n_out=83, msg_steps=2, seed=4)
+  model = graphcast.GraphCast(cfg, task, params=params)
+  fn = lambda rng, inputs, targets_template, forcings: model(inputs, targets_template, forcings)
+  traj = rollout.chunked_prediction(fn, None, inputs, template, forcings)
+  sink = rollout.PinnedPredictionSink(depth=2)
+  got, slots = [], []
+  for chunk in rollout.chunked_prediction_generator(fn, None, inputs, template, 1, forcings):
+    if slots:                      # consume the previous chunk while this step's copies are in flight
+      prev = slots[-1]
+      sink._done[(sink._n - 1) % 2].synchronize()
+      got.append({k: v.numpy().copy() for k, v in prev.items()})
+    slots.append(sink(chunk))
+  sink.wait()
+  got.append({k: v.numpy().copy() for k, v in slots[-1].items()})
+  assert len(got) == 4 and all(v.is_pinned() for v in slots[0].values())
+  assert slots[0] is slots[2] and slots[0] is not slots[1]
+  for k, step in enumerate(got):
+    for name, val in step.items():
+      want = np.asarray(traj.data_vars[name].values)
+      t_axis = traj.data_vars[name].dims.index("time")
+      assert np.array_equal(val, np.take(want, [k], axis=t_axis)), (k, name)
+  with pytest.raises(TypeError):
+    sink(traj)                     # host-resident data is refused
+
+
 def test_rollout_with_device_generated_forcings_matches_host_forcings():
   """`generate_forcings`: TISR by the CUDA kernel + progress features per chunk, no forcing fields
   uploaded, against the same rollout fed with the host (numpy) mirror of the reference's forcing
