@@ -238,6 +238,57 @@ class PartitionedEngine:
     eng.run_stage("decode")
     return eng.grid_out[:self.local.grid_owned.size]
 
+  def step_from_host(self, host_planes, host_out):
+    """End-to-end step with HOST buffers, pipelined over successive calls.
+
+    host_planes: pinned fp32 [c_in, n_grid_local] (this rank's owned + halo grid columns);
+    host_out: pinned fp32 [n_out, n_grid_owned].  The upload runs on a copy stream into one of two
+    staging buffers, the download on a second side stream out of one of two result buffers, so call
+    i + 1's upload and call i's download overlap the kernels of the neighbouring steps (the host
+    returns as soon as everything is queued).  Returns the event after which `host_out` is complete."""
+    torch, eng = self._torch, self.engine
+    n_owned = int(self.local.grid_owned.size)
+    if tuple(host_planes.shape) != (eng.c_in, eng.num_grid) or tuple(host_out.shape) != (eng.n_out, n_owned) \
+        or not (host_planes.is_pinned() and host_out.is_pinned()):
+      raise ValueError(f"expected pinned fp32 host buffers [{eng.c_in}, {eng.num_grid}] and "
+                       f"[{eng.n_out}, {n_owned}]")
+    io = getattr(self, "_io", None)
+    if io is None:
+      f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=eng.device)
+      io = self._io = {
+          "h2d": torch.cuda.Stream(eng.device), "d2h": torch.cuda.Stream(eng.device), "n": 0,
+          "dev_in": [f(eng.c_in, eng.num_grid) for _ in range(2)],
+          "dev_out": [f(eng.n_out, n_owned) for _ in range(2)],
+          "in_free": [None, None], "out_free": [None, None]}
+    b = io["n"] % 2
+    io["n"] += 1
+    compute = torch.cuda.current_stream(eng.device)
+    with torch.cuda.stream(io["h2d"]):
+      if io["in_free"][b] is not None:
+        io["h2d"].wait_event(io["in_free"][b])        # the step two calls ago has packed this buffer
+      io["dev_in"][b].copy_(host_planes, non_blocking=True)
+      uploaded = torch.cuda.Event()
+      uploaded.record(io["h2d"])
+    compute.wait_event(uploaded)
+    self.step(io["dev_in"][b])
+    io["in_free"][b] = torch.cuda.Event()
+    io["in_free"][b].record(compute)                  # conservative: after the whole step
+    if io["out_free"][b] is not None:
+      compute.wait_event(io["out_free"][b])           # its previous download has finished
+    with eng._on_device():
+      self._native.check(self._lib.gcb_unpack_grid_outputs(
+          eng.grid_out.data_ptr(), 256, eng.n_out, n_owned, None, None, None, None,
+          io["dev_out"][b].data_ptr(), eng._stream()), "gcb_unpack_grid_outputs")
+    unpacked = torch.cuda.Event()
+    unpacked.record(compute)
+    with torch.cuda.stream(io["d2h"]):
+      io["d2h"].wait_event(unpacked)
+      host_out.copy_(io["dev_out"][b], non_blocking=True)
+      done = torch.cuda.Event()
+      done.record(io["d2h"])
+    io["out_free"][b] = done
+    return done
+
   def halo_ms_per_exchange(self) -> Optional[float]:
     if not self._events:
       return None
