@@ -152,3 +152,28 @@ def test_autoregressive_predictor_unrolls_like_the_rollout():
     ar(inputs, template, xs.Dataset(coords={"time": tt}))
   with pytest.raises(ValueError, match="both targets and forcings"):
     ar(inputs, template, xs.Dataset({"toa": forcings["toa"], "t2m": template["t2m"]}, coords={"time": tt}))
+
+
+def test_extend_targets_template_keeps_batched_datetime():
+  """`datetime` with dims (batch, time) -- what `generate_forcings` reads -- is extended along time and
+  keeps its batch axis (utils/rollout.py:607-640 extends every time-indexed coordinate)."""
+  template = xs.Dataset(
+      {"t": xs.DataArray(np.zeros((1, 2, 3, 4), np.float32), ("batch", "time", "lat", "lon"))},
+      coords={"time": (("time",), np.array([6, 12], "timedelta64[h]").astype("timedelta64[ns]")),
+              "lat": (("lat",), np.arange(3.0)), "lon": (("lon",), np.arange(4.0))})
+  t0 = np.datetime64("2021-03-17T06:00:00")
+  dt = (t0 + np.asarray(template.coords["time"][1])).astype("datetime64[ns]")[None, :]
+  template = template.assign_coords(datetime=(("batch", "time"), dt))
+  out = rollout.extend_targets_template(template, 5)
+  dims, vals = out.coords["datetime"]
+  assert tuple(dims) == ("batch", "time") and np.asarray(vals).shape == (1, 5)
+  step = np.timedelta64(6, "h")
+  assert (np.diff(np.asarray(vals)[0]) == step).all() and np.asarray(vals)[0, 0] == t0 + step
+
+
+def test_pinned_prediction_sink_refuses_host_resident_chunks():
+  sink = rollout.PinnedPredictionSink(depth=3)
+  chunk = xs.Dataset({"t": xs.DataArray(np.zeros((1, 1, 3, 4), np.float32), ("batch", "time", "lat", "lon"))})
+  with pytest.raises(TypeError):
+    sink(chunk)
+  sink.wait()                       # nothing queued: a no-op
