@@ -14,8 +14,10 @@ Ownership
   edge        the owner of its receiver (all three graphs)
 Local tables of rank r
   mesh  [owned | padding to a multiple of 128 | halo]   halo = remote senders of owned multi-mesh
-        and mesh2grid edges, grouped by owner: a peer's rows arrive contiguously, straight into the
-        fp32 table; the 128-row alignment lets the halo part of the operand image be rebuilt alone
+        and mesh2grid edges, grouped by owner: a peer's rows arrive contiguously -- as rows of the
+        operand image (default: image-only latents, gcb_image_rows_pack / _unpack) or, with fp32
+        masters, straight into the fp32 table; the 128-row alignment gives the halo its own tiles
+        of the operand image
   grid  [owned | halo]    halo = remote senders of owned grid2mesh edges; their encoder latents are
         recomputed locally from the raw inputs (a per-node MLP) instead of being exchanged
 A rank's local arrays form an ordinary `StaticGraph` (local numbering) for `engine.Engine`, which
