@@ -1,8 +1,8 @@
 """Diagnostic: what does precision="bf16" compute?  Layer level (device vs bf16-rounded-operand
 fp64 product) and step level (device vs oracle.gnn.Bf16OperandOracle, several engine layouts)."""
 import ctypes as C, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 import numpy as np, torch
 import _cases, test_gpu_chain as tc
 from graphcast_b200 import _native, engine

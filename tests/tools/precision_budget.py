@@ -13,7 +13,7 @@ fp64 oracle (the parity metric of tests/ and bench.py).
           x2a = two products, activations rounded to bf16 a_hi*(w_hi+w_lo)
           x3  = the product's parity mode (drops only a_lo*w_lo), for scale
 
-  python tools/precision_budget.py --workload sample_2deg_13lvl [--out profiles/r02_precision_budget.md]
+  python tests/tools/precision_budget.py --workload sample_2deg_13lvl [--out profiles/r02_precision_budget.md]
 """
 import argparse
 import os
@@ -23,7 +23,7 @@ import time
 import numpy as np
 import torch
 
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, REPO)
 
 from graphcast_b200 import graph as graph_lib, graphcast, synthetic   # noqa: E402
@@ -118,7 +118,7 @@ def main():
   lines = [f"# Precision budget per layer group -- {args.workload}, 16 message-passing steps, Haiku-default weights",
            "",
            "Error = max|y - y_ref| / max|y_ref| of the step output vs the exact fp64 oracle when ONLY the named",
-           "group computes its contractions with the reduced products (tools/precision_budget.py; parity gate 1e-4).",
+           "group computes its contractions with the reduced products (tests/tools/precision_budget.py; parity gate 1e-4).",
            "",
            "| layer group | " + " | ".join(modes) + " |", "|---|" + "---|" * len(modes)]
   for name, errs in rows:

@@ -1,13 +1,13 @@
 """Premise of bench.py's CPU sample (oracle/sampled_step.py): full fp32 oracle step vs row-sampled
 step / fraction, on this host.
 
-  python tools/validate_cpu_sample.py [threads] [resolution]     # resolution 1.0 (default) or 0.25
+  python tests/tools/validate_cpu_sample.py [threads] [resolution]     # resolution 1.0 (default) or 0.25
 
 1.0: BASELINE config 1 (1 deg, mesh 5, 13 levels) in full, 3 repetitions per fraction.
 0.25: ONE full pass of the benchmark workload (0.25 deg, mesh 6, 37 levels: 29.3 TFLOP) against the
 sample bench.py times (fractions 1/32 and 1/16)."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from graphcast_b200 import graph as graph_lib, graphcast, synthetic
 from oracle import gnn, sampled_step
