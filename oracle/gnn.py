@@ -64,6 +64,25 @@ class Oracle:
     """x @ w.  Hook so tests can emulate reduced-precision tensor-core products."""
     return x @ w
 
+  # Further hooks (identity arithmetic here) so that a subclass can place roundings where a
+  # reduced-precision execution of the reference has them (ReferenceBf16Oracle below).
+  def bias_add(self, x, b):
+    return x + b
+
+  def activation(self, x):
+    return swish(x)
+
+  def normalize(self, x, scale, offset):
+    return layer_norm(x, scale, offset)
+
+  def add(self, a, b):
+    """Residual connections (deep_typed_graph_net.py:372-393, graphcast.py:596-604,668-672)."""
+    return a + b
+
+  def aggregate(self, gnn: str, data, segment_ids, num_segments):
+    """jraph.segment_sum of the edge messages of GNN `gnn` (typed_graph_net.py:532-538)."""
+    return self.segment_sum(data, segment_ids, num_segments)
+
   # hk.nets.MLP (+ optional hk.LayerNorm) on the concatenation of `args`.
   def mlp(self, stem: str, args, use_layer_norm: bool = True):
     x = torch.cat(list(args), dim=-1)
@@ -71,12 +90,12 @@ class Oracle:
     while f"{stem}_mlp/~/linear_{i}" in self.p:
       lin = self.p[f"{stem}_mlp/~/linear_{i}"]
       if i > 0:
-        x = swish(x)
-      x = self.matmul(x, lin["w"]) + lin["b"]
+        x = self.activation(x)
+      x = self.bias_add(self.matmul(x, lin["w"]), lin["b"])
       i += 1
     if use_layer_norm:
       ln = self.p[f"{stem}_layer_norm"]
-      x = layer_norm(x, ln["scale"], ln["offset"])
+      x = self.normalize(x, ln["scale"], ln["offset"])
     return x
 
   @staticmethod
@@ -110,9 +129,9 @@ class Oracle:
     e1 = self.mlp(mlp_name(g, "encoder_edges_", "grid2mesh"), [bcast(graph["g2m_edge_feats"])])
     s1, r1 = self._idx(graph["g2m_senders"]), self._idx(graph["g2m_receivers"])
     m1 = self.mlp(mlp_name(g, "processor_edges_0_", "grid2mesh"), [e1, vg0[s1], vm0[r1]])
-    agg1 = self.segment_sum(m1, r1, n_mesh)        # f32_aggregation is a no-op in f32
-    vm1 = vm0 + self.mlp(mlp_name(g, "processor_nodes_0_", "mesh_nodes"), [vm0, agg1])
-    vg1 = vg0 + self.mlp(mlp_name(g, "processor_nodes_0_", "grid_nodes"), [vg0])
+    agg1 = self.aggregate(g, m1, r1, n_mesh)       # f32_aggregation is a no-op in f32
+    vm1 = self.add(vm0, self.mlp(mlp_name(g, "processor_nodes_0_", "mesh_nodes"), [vm0, agg1]))
+    vg1 = self.add(vg0, self.mlp(mlp_name(g, "processor_nodes_0_", "grid_nodes"), [vg0]))
     if inter is not None:
       inter.update(vg0=vg0, vm0=vm0, e1=e1, m1=m1, agg1=agg1, vm1=vm1, vg1=vg1)
     return vm1, vg1
@@ -128,9 +147,9 @@ class Oracle:
     g = "mesh_gnn"
     s2, r2 = self._idx(graph["mesh_senders"]), self._idx(graph["mesh_receivers"])
     m = self.mlp(mlp_name(g, f"processor_edges_{k}_", "mesh"), [e, v[s2], v[r2]])
-    agg = self.segment_sum(m, r2, v.shape[0])
-    v_new = v + self.mlp(mlp_name(g, f"processor_nodes_{k}_", "mesh_nodes"), [v, agg])
-    return v_new, e + m
+    agg = self.aggregate(g, m, r2, v.shape[0])
+    v_new = self.add(v, self.mlp(mlp_name(g, f"processor_nodes_{k}_", "mesh_nodes"), [v, agg]))
+    return v_new, self.add(e, m)
 
   def num_message_steps(self) -> int:
     k = 0
@@ -157,8 +176,8 @@ class Oracle:
     e3 = self.mlp(mlp_name(g, "encoder_edges_", "mesh2grid"), [bcast(graph["m2g_edge_feats"])])
     s3, r3 = self._idx(graph["m2g_senders"]), self._idx(graph["m2g_receivers"])
     m3 = self.mlp(mlp_name(g, "processor_edges_0_", "mesh2grid"), [e3, v[s3], vg1[r3]])
-    agg3 = self.segment_sum(m3, r3, n_grid)
-    vg2 = vg1 + self.mlp(mlp_name(g, "processor_nodes_0_", "grid_nodes"), [vg1, agg3])
+    agg3 = self.aggregate(g, m3, r3, n_grid)
+    vg2 = self.add(vg1, self.mlp(mlp_name(g, "processor_nodes_0_", "grid_nodes"), [vg1, agg3]))
     out = self.mlp(mlp_name(g, "decoder_nodes_", "grid_nodes"), [vg2], use_layer_norm=False)
     if inter is not None:
       inter.update(vg2=vg2)
@@ -195,6 +214,58 @@ class Bf16OperandOracle(Oracle):
   def matmul(self, x, w):
     r = lambda t: t.to(torch.float32).to(torch.bfloat16).to(self.dtype)
     return r(x) @ r(w)
+
+
+class ReferenceBf16Oracle(Oracle):
+  """The reference's OWN bf16 execution, emulated op by op (what `casting.Bfloat16Cast` makes of the
+  model): inputs and parameters are bfloat16 (utils/casting.py:53-58 with `_all_inputs_to_bfloat16`
+  :135-145 and `bfloat16_variable_view` :156-205), so every jnp op returns a bfloat16 array -- the linear layers
+  (fp32 accumulation inside the dot, result rounded), bias adds, `jax.nn.swish` (sigmoid, then the
+  product), `hk.LayerNorm` (mean, variance, rsqrt, scale, shift: each a bf16 result), the residual adds
+  and the segment sums; only grid2mesh aggregates in fp32 (`f32_aggregation`, graphcast.py:215,232,260
+  with utils/legacy/deep_typed_graph_net.py:273-288) before rounding the sum.  Every rounding is round-to-nearest-even of
+  a value computed in fp32 from bf16 operands, i.e. the semantics of the individual XLA ops; a fused
+  XLA executable may keep some intermediates wider, and a bf16 scatter-add may round after every
+  addend, so this is one admissible execution, not a bit-level model of any backend.
+
+  Used to place the product's "bf16" mode (Bf16OperandOracle: bf16 operands, everything else fp32)
+  against what the reference computes under `Bfloat16Cast` (tests/test_oracle.py)."""
+
+  F32_AGGREGATION = ("grid2mesh_gnn",)
+
+  def __init__(self, params: Params):
+    super().__init__(params, torch.float32)
+    self.p = {k: {n: self._r(a) for n, a in v.items()} for k, v in self.p.items()}
+
+  @staticmethod
+  def _r(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+  def _t(self, a):
+    return self._r(super()._t(a))
+
+  def matmul(self, x, w):
+    return self._r(x @ w)
+
+  def bias_add(self, x, b):
+    return self._r(x + b)
+
+  def activation(self, x):
+    return self._r(x * self._r(torch.sigmoid(x)))
+
+  def normalize(self, x, scale, offset, eps: float = 1e-5):
+    r = self._r
+    mean = r(x.mean(dim=-1, keepdim=True))
+    var = r(((x - x.mean(dim=-1, keepdim=True)) ** 2).mean(dim=-1, keepdim=True))   # jnp.var: fp32 inside
+    inv = r(scale * r(torch.rsqrt(r(var + eps))))
+    return r(r(inv * r(x - mean)) + offset)
+
+  def add(self, a, b):
+    return self._r(a + b)
+
+  def aggregate(self, gnn, data, segment_ids, num_segments):
+    # fp32 accumulation either way here (optimistic for the GNNs without f32_aggregation)
+    return self._r(self.segment_sum(data, segment_ids, num_segments))
 
 
 def truncated_normal(rng: np.random.Generator, shape, stddev: float) -> np.ndarray:

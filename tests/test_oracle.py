@@ -1,6 +1,7 @@
-"""Oracle self-checks (the GNN forward is a restatement: PARITY UNPINNED against the
-executed reference; these tests pin it against independent formulations and against
-a committed regression vector)."""
+"""Oracle self-checks.  The GNN forward is pinned against the EXECUTED reference wiring in
+tests/test_reference_gnn_golden.py and tests/test_reference_gnn_latent512.py; the tests here check
+it against independent formulations, a committed regression vector, and place the reduced-precision
+emulations (the product's "bf16" mode, the reference's own bf16 execution) against the exact result."""
 import os
 
 import numpy as np
@@ -65,3 +66,43 @@ def test_param_inventory_matches_survey_appendix_b():
   assert p["mesh_gnn/~_networks_builder/processor_edges_3_mesh_mlp/~/linear_0"]["w"].shape == (1536, 512)
   assert p["mesh2grid_gnn/~_networks_builder/decoder_nodes_grid_nodes_mlp/~/linear_1"]["w"].shape == (512, 227)
   assert "mesh2grid_gnn/~_networks_builder/decoder_nodes_grid_nodes_layer_norm" not in p
+
+
+def test_identity_hooks_do_not_change_the_forward():
+  """The rounding hooks of the base class are identities: a subclass that spells them out
+  reproduces Oracle.forward bit for bit (the pinned goldens therefore cover the hooked code)."""
+  class Spelled(gnn.Oracle):
+    def bias_add(self, x, b): return x + b
+    def activation(self, x): return x * torch.sigmoid(x)
+    def normalize(self, x, scale, offset): return gnn.layer_norm(x, scale, offset)
+    def add(self, a, b): return a + b
+    def aggregate(self, name, data, ids, n): return gnn.Oracle.segment_sum(data, ids, n)
+  g, params, x = _cases.small_case(c_in=11, n_out=7, msg_steps=2)
+  a = gnn.Oracle(params, torch.float64).forward(g.as_dict(), x)
+  b = Spelled(params, torch.float64).forward(g.as_dict(), x)
+  assert torch.equal(a, b)
+
+
+def test_bf16_mode_is_at_least_as_accurate_as_the_reference_bf16_execution():
+  """`precision="bf16"` (bf16 operands, fp32 everything else: Bf16OperandOracle) against the
+  reference's own execution under casting.Bfloat16Cast (every op result rounded to bfloat16,
+  fp32 aggregation only in grid2mesh: ReferenceBf16Oracle), both measured against the exact fp64
+  step: the product's mode must not be the less accurate of the two, and both stay far outside the
+  1e-4 gate of the parity mode (which is why bf16x3 is the default)."""
+  g, params, x = _cases.small_case(c_in=31, n_out=23, msg_steps=4, randomize_affine=False)
+  gd = g.as_dict()
+  exact = gnn.Oracle(params, torch.float64).forward(gd, x)
+  scale = exact.abs().max().item()
+  err = lambda y: (y.to(torch.float64) - exact).abs().max().item() / scale
+  ours = err(gnn.Bf16OperandOracle(params, torch.float32).forward(gd, x))
+  ref = gnn.ReferenceBf16Oracle(params)
+  theirs = err(ref.forward(gd, x))
+  print(f"bf16 mode {ours:.2e}  reference bf16 execution {theirs:.2e}")
+  assert 1e-4 < ours < 3e-2 and 1e-4 < theirs < 1e-1
+  assert ours <= theirs
+  # every value the reference-style execution produces is a bfloat16 number
+  y, inter = ref.forward(gd, x, return_intermediates=True)
+  for name in ("vm1", "vg1", "v_mesh", "vg2"):
+    t = inter[name]
+    assert torch.equal(t, t.to(torch.bfloat16).to(torch.float32)), name
+  assert torch.equal(y, y.to(torch.bfloat16).to(torch.float32))
