@@ -133,7 +133,9 @@ int gcb_rows_to_image(const float* src, int32_t ld, int32_t fan, int64_t rows, i
 int gcb_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, int64_t n, float* dst,
                     int32_t ld_dst, int32_t width, void* stream);
 
-/* Same for a latent stream that exists only as an operand image of a [*, 512] matrix.  A packed row is
+/* Same (reference analogue: utils/gather_scatter_ops.py:423 all_gather before a sharded gather, and
+ * its shard-local fast path :102-144) for a latent stream that exists only as an operand image of a
+ * [*, 512] matrix.  A packed row is
  * 2048 bytes (per 8-column piece the image's 16 bytes of bf16 hi, then its 16 bytes of lo):
  *   pack:   buf[i] = image row idx[i]                 (send side)
  *   unpack: image row first_row + i = buf[i]          (receive side; bit-identical to the owner's) */
