@@ -82,3 +82,67 @@ def test_partition_sizes_at_the_benchmark_resolution():
   assert sum(st["mesh_edges"]) == 327660 and sum(st["g2m_edges"]) == 1618818
   assert max(st["halo_bytes_per_step"]) <= 1.4e6
   print(st)
+
+
+# ---- the same step on two real processes (gloo), with the exchange PartitionedEngine issues ----------
+
+def _gloo_worker(rank, world, port, q):
+  import os
+  import torch.distributed as dist
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  try:
+    torch.set_num_threads(2)
+    g, params, x = _cases.small_case(c_in=31, n_out=23, msg_steps=2, batch=1)
+    x = x.astype(np.float64)
+    orc = oracle_gnn.Oracle(params, torch.float64)
+    lg = partitioned.build_local_graph(g, world, rank)
+    gd = lg.graph.as_dict()
+    send_rows = torch.as_tensor(lg.send_rows, dtype=torch.int64)
+    n_halo = int(lg.mesh_halo.size)
+
+    def exchange(table):
+      """PartitionedEngine.exchange_halo with torch ops in place of the pack / unpack kernels:
+      gather the owned boundary rows (grouped by peer), ONE all_to_all_single with the plan's split
+      sizes, store the received rows behind the 128-aligned owned block."""
+      flat = table.reshape(table.shape[0], -1)
+      send = flat[send_rows].contiguous()
+      recv = torch.empty([n_halo, flat.shape[1]], dtype=flat.dtype)
+      dist.all_to_all_single(recv, send, output_split_sizes=lg.recv_counts,
+                             input_split_sizes=lg.send_counts)
+      out = table.clone()
+      out[lg.mesh_owned_pad:lg.mesh_owned_pad + n_halo] = recv.reshape((n_halo,) + tuple(table.shape[1:]))
+      return out
+
+    vm, vg = orc.encoder(gd, x[lg.local_grid_ids])
+    v = exchange(vm)
+    e = orc.processor_embed(gd, x.shape[1])
+    for k in range(orc.num_message_steps()):
+      v, e = orc.processor_step(gd, v, e, k)
+      v = exchange(v)
+    out = orc.decoder(gd, v, vg)[:lg.grid_owned.size]
+    q.put((rank, lg.grid_owned, out.numpy()))
+  finally:
+    dist.destroy_process_group()
+
+
+def test_partitioned_step_on_two_gloo_ranks_equals_the_full_step():
+  import socket
+  import torch.multiprocessing as mp
+  s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  parts = [q.get(timeout=600) for _ in procs]
+  for p in procs:
+    p.join(timeout=60)
+    assert p.exitcode == 0
+  g, params, x = _cases.small_case(c_in=31, n_out=23, msg_steps=2, batch=1)
+  ref = oracle_gnn.Oracle(params, torch.float64).forward(g.as_dict(), x.astype(np.float64)).numpy()
+  y = np.full_like(ref, np.nan)
+  for _, owned, out in parts:
+    y[owned] = out
+  assert np.isfinite(y).all()
+  assert np.abs(y - ref).max() / np.abs(ref).max() < 1e-12
